@@ -1,0 +1,195 @@
+// jdsp_device.cuh -- device-side building blocks shared by every kernel of the spectral hot path:
+// complex helpers, in-register DFT-2/4/8/16 butterflies, and a shared-memory-staged Stockham
+// "group FFT" in which each thread keeps E (<=16) complex points in registers per pass.
+//
+// What this replaces in the reference: the radix-2 DIT loops of FFTProcess/Bitrev
+// (FFTAlgorithm_ver2.cpp:94-149,186-207) and the fftw_execute call sites of the four
+// FFTW-based programs (e.g. SpectralSubtraction_final.cpp:229-230,244-245).  Same transform
+// (unnormalised DFT, sign -1 forward / +1 backward), different algorithm: autosort Stockham,
+// radix 16 in registers, one padded shared-memory exchange per pass, no bit-reversal pass.
+#pragma once
+#ifdef JDSP_EMUL
+#include "cuda_emul.h"
+#define JDSP_DYN_SMEM(name) unsigned char *name = jdsp_emul_dyn_smem
+#define JDSP_LAUNCH_PTR(kfn, grid, block, smem, stream, ...) \
+    jdsp_emul::launch((grid), (block), (smem), [&]() { kfn(__VA_ARGS__); })
+#else
+#include <cuda_runtime.h>
+#define JDSP_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define JDSP_LAUNCH_PTR(kfn, grid, block, smem, stream, ...) kfn<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+#include <stdint.h>
+
+#define JDSP_DEV __device__ __forceinline__
+
+namespace jdsp {
+
+// ---- complex value, laid out exactly like the reference's COMPLEX / fftw_complex (re, im) -------
+template <typename T> struct cx;
+template <> struct alignas(8) cx<float> { float x, y; };
+template <> struct alignas(16) cx<double> { double x, y; };
+
+template <typename T> JDSP_DEV cx<T> cmake(T a, T b) { cx<T> r; r.x = a; r.y = b; return r; }
+template <typename T> JDSP_DEV cx<T> cadd(cx<T> a, cx<T> b) { return cmake<T>(a.x + b.x, a.y + b.y); }
+template <typename T> JDSP_DEV cx<T> csub(cx<T> a, cx<T> b) { return cmake<T>(a.x - b.x, a.y - b.y); }
+// a * (wr + j*wi)
+template <typename T> JDSP_DEV cx<T> cmulw(cx<T> a, T wr, T wi) { return cmake<T>(a.x * wr - a.y * wi, a.x * wi + a.y * wr); }
+// a * w, or a * conj(w) when CONJ
+template <bool CONJ, typename T> JDSP_DEV cx<T> cmul(cx<T> a, cx<T> w) {
+    return CONJ ? cmulw<T>(a, w.x, -w.y) : cmulw<T>(a, w.x, w.y);
+}
+// multiply by -j (forward rotation) or +j (inverse)
+template <bool INV, typename T> JDSP_DEV cx<T> crot(cx<T> a) { return INV ? cmake<T>(-a.y, a.x) : cmake<T>(a.y, -a.x); }
+
+// ---- in-register DFTs: natural order in, natural order out, unnormalised ----------------------
+template <bool INV, typename T> JDSP_DEV void dft2(cx<T> &a, cx<T> &b) {
+    const cx<T> s = cadd(a, b), d = csub(a, b);
+    a = s; b = d;
+}
+template <bool INV, typename T> JDSP_DEV void dft4(cx<T> &a0, cx<T> &a1, cx<T> &a2, cx<T> &a3) {
+    const cx<T> t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = crot<INV>(csub(a1, a3));
+    a0 = cadd(t0, t2); a2 = csub(t0, t2);
+    a1 = cadd(t1, t3); a3 = csub(t1, t3);
+}
+// multiply by exp(-+ 2*pi*j * m/16): constants folded at compile time
+template <bool INV, int M, typename T> JDSP_DEV cx<T> cw16(cx<T> a) {
+    constexpr int m = ((M % 16) + 16) % 16;
+    const T c1 = (T)0.92387953251128675613, s1 = (T)0.38268343236508977173, r = (T)0.70710678118654752440;
+    T wr, wi;  // forward twiddle exp(-2*pi*j*m/16)
+    if (m == 0) return a;
+    if (m == 4) return crot<INV>(a);
+    if (m == 8) return cmake<T>(-a.x, -a.y);
+    if (m == 12) return crot<!INV>(a);
+    switch (m) {
+        case 1: wr = c1; wi = -s1; break;
+        case 2: wr = r; wi = -r; break;
+        case 3: wr = s1; wi = -c1; break;
+        case 5: wr = -s1; wi = -c1; break;
+        case 6: wr = -r; wi = -r; break;
+        case 7: wr = -c1; wi = -s1; break;
+        case 9: wr = -c1; wi = s1; break;
+        case 10: wr = -r; wi = r; break;
+        case 11: wr = -s1; wi = c1; break;
+        case 13: wr = s1; wi = c1; break;
+        case 14: wr = r; wi = r; break;
+        default: wr = c1; wi = s1; break;  // 15
+    }
+    return cmulw<T>(a, wr, INV ? -wi : wi);
+}
+template <bool INV, typename T> JDSP_DEV void dft8(cx<T> (&a)[8]) {
+    dft4<INV>(a[0], a[2], a[4], a[6]);  // even samples -> E[0..3] in a[0],a[2],a[4],a[6]
+    dft4<INV>(a[1], a[3], a[5], a[7]);  // odd samples  -> O[0..3] in a[1],a[3],a[5],a[7]
+    const cx<T> e0 = a[0], e1 = a[2], e2 = a[4], e3 = a[6];
+    const cx<T> o0 = a[1], o1 = cw16<INV, 2>(a[3]), o2 = cw16<INV, 4>(a[5]), o3 = cw16<INV, 6>(a[7]);
+    a[0] = cadd(e0, o0); a[4] = csub(e0, o0);
+    a[1] = cadd(e1, o1); a[5] = csub(e1, o1);
+    a[2] = cadd(e2, o2); a[6] = csub(e2, o2);
+    a[3] = cadd(e3, o3); a[7] = csub(e3, o3);
+}
+template <bool INV, typename T> JDSP_DEV void dft16(cx<T> (&a)[16]) {
+    // n = 4*n1 + n2, k = k1 + 4*k2.  Column DFT-4s over n1, twiddle W16^(n2*k1), row DFT-4s over n2.
+    dft4<INV>(a[0], a[4], a[8], a[12]);
+    dft4<INV>(a[1], a[5], a[9], a[13]);
+    dft4<INV>(a[2], a[6], a[10], a[14]);
+    dft4<INV>(a[3], a[7], a[11], a[15]);
+    // a[n2 + 4*k1] now holds column result (n2, k1)
+    a[5] = cw16<INV, 1>(a[5]); a[9] = cw16<INV, 2>(a[9]); a[13] = cw16<INV, 3>(a[13]);
+    a[6] = cw16<INV, 2>(a[6]); a[10] = cw16<INV, 4>(a[10]); a[14] = cw16<INV, 6>(a[14]);
+    a[7] = cw16<INV, 3>(a[7]); a[11] = cw16<INV, 6>(a[11]); a[15] = cw16<INV, 9>(a[15]);
+    dft4<INV>(a[0], a[1], a[2], a[3]);      // k1 = 0 -> X[0], X[4], X[8], X[12]
+    dft4<INV>(a[4], a[5], a[6], a[7]);      // k1 = 1 -> X[1], X[5], X[9], X[13]
+    dft4<INV>(a[8], a[9], a[10], a[11]);    // k1 = 2
+    dft4<INV>(a[12], a[13], a[14], a[15]);  // k1 = 3
+    // slot 4*k1 + k2 holds X[k1 + 4*k2]: transpose the 4x4 (register renaming only)
+    cx<T> t;
+    t = a[1]; a[1] = a[4]; a[4] = t;
+    t = a[2]; a[2] = a[8]; a[8] = t;
+    t = a[3]; a[3] = a[12]; a[12] = t;
+    t = a[6]; a[6] = a[9]; a[9] = t;
+    t = a[7]; a[7] = a[13]; a[13] = t;
+    t = a[11]; a[11] = a[14]; a[14] = t;
+}
+template <int R, bool INV, typename T> JDSP_DEV void dftR(cx<T> (&a)[R]) {
+    if constexpr (R == 2) dft2<INV>(a[0], a[1]);
+    else if constexpr (R == 4) dft4<INV>(a[0], a[1], a[2], a[3]);
+    else if constexpr (R == 8) dft8<INV>(a);
+    else if constexpr (R == 16) dft16<INV>(a);
+    else static_assert(R == 1, "unsupported radix");
+}
+
+// ---- padded shared-memory layout: one spare element every 16 keeps radix-16 strides conflict-free
+JDSP_DEV int pad16(int e) { return e + (e >> 4); }
+__host__ __device__ constexpr int padded_len(int n) { return n + (n >> 4); }
+
+template <int SYNC> JDSP_DEV void group_sync() {
+    if constexpr (SYNC == 0) __syncwarp(); else __syncthreads();
+}
+
+// One Stockham pass in registers.  reg[m] holds element (t + G*m) of the current sequence,
+// G = NC/E threads per transform.  Butterfly u (of U = E/R) uses reg[u + i*U], i < R, i.e. sequence
+// elements j + i*NC/R with j = t + G*u; k = j mod NS selects the twiddle W_{NS*R}^{i*k} taken from
+// the full-size table tw[q] = exp(-2*pi*j*q/NC).
+template <typename T, int NC, int E, int R, int NS, bool INV>
+JDSP_DEV void fft_pass_compute(cx<T> (&reg)[E], int t, const cx<T> *__restrict__ tw) {
+    constexpr int G = NC / E, U = E / R;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        cx<T> v[R];
+#pragma unroll
+        for (int i = 0; i < R; ++i) v[i] = reg[u + i * U];
+        if constexpr (NS > 1) {
+            const int k = (t + G * u) & (NS - 1);
+            constexpr int STEP = NC / (NS * R);
+#pragma unroll
+            for (int i = 1; i < R; ++i) v[i] = cmul<INV>(v[i], tw[i * k * STEP]);
+        }
+        dftR<R, INV>(v);
+#pragma unroll
+        for (int i = 0; i < R; ++i) reg[u + i * U] = v[i];
+    }
+}
+// scatter the outputs of a non-final pass to their Stockham positions (padded)
+template <typename T, int NC, int E, int R, int NS>
+JDSP_DEV void fft_pass_store(const cx<T> (&reg)[E], int t, cx<T> *buf) {
+    constexpr int G = NC / E, U = E / R;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int j = t + G * u, k = j & (NS - 1);
+        const int base = (j - k) * R + k;
+#pragma unroll
+        for (int i = 0; i < R; ++i) buf[pad16(base + i * NS)] = reg[u + i * U];
+    }
+}
+template <typename T, int NC, int E> JDSP_DEV void fft_load_regs(cx<T> (&reg)[E], int t, const cx<T> *buf) {
+    constexpr int G = NC / E;
+#pragma unroll
+    for (int m = 0; m < E; ++m) reg[m] = buf[pad16(t + G * m)];
+}
+template <typename T, int NC, int E> JDSP_DEV void fft_store_regs(const cx<T> (&reg)[E], int t, cx<T> *buf) {
+    constexpr int G = NC / E;
+#pragma unroll
+    for (int m = 0; m < E; ++m) buf[pad16(t + G * m)] = reg[m];
+}
+
+// Whole transform.  In: reg[m] = x[t + G*m].  Out: reg[m] = X[t + G*m] (natural order).
+// buf: padded_len(NC) elements of shared memory private to the group; may hold garbage on entry but
+// nobody else may be reading it.  SYNC 0: the group lives inside one warp; 1: the group is the CTA.
+template <typename T, int NC, int E, bool INV, int SYNC, int NS = 1>
+JDSP_DEV void group_fft(cx<T> (&reg)[E], int t, cx<T> *buf, const cx<T> *__restrict__ tw) {
+    constexpr int REM = NC / NS;
+    constexpr int R = REM < E ? REM : E;
+    fft_pass_compute<T, NC, E, R, NS, INV>(reg, t, tw);
+    if constexpr (NS * R < NC) {
+        if constexpr (NS > 1) group_sync<SYNC>();  // every thread has finished loading before anyone overwrites
+        fft_pass_store<T, NC, E, R, NS>(reg, t, buf);
+        group_sync<SYNC>();
+        fft_load_regs<T, NC, E>(reg, t, buf);
+        group_fft<T, NC, E, INV, SYNC, NS * R>(reg, t, buf, tw);
+    }
+}
+
+// ---- small numeric helpers ---------------------------------------------------------------------------
+// (short)(double) of the reference: truncate toward zero, keep the low 16 bits
+JDSP_DEV int16_t trunc16(float v) { return (int16_t)__float2int_rz(v); }
+
+}  // namespace jdsp
