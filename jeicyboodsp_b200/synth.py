@@ -38,7 +38,7 @@ def denoise_stream(stream: int, n: int, fs: float = 16_000.0, sigma: float = 40.
 def denoise_streams_torch(n_streams: int, n: int, device, stream0: int = 0, fs: float = 16_000.0,
                           sigma: float = 40.0, amp: float = 6000.0, seed: int = 2, chunk: int = 256):
     """Device-resident [n_streams, n] int16 of the same family (torch generator, so the noise differs
-    from the numpy version; parity streams are copied back to the host and fed to the oracle)."""
+    from the numpy version; parity streams are copied back to the host by the tests)."""
     import torch
 
     g = torch.Generator(device=device)

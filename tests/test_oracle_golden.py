@@ -1,0 +1,52 @@
+"""Oracle restatement vs the committed fixtures produced by the reference's own code
+(tests/golden/make_golden.py ran the unmodified programs of oracle/_ref)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle.oracle import DenoiseParams, MfccParams
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_fft_golden(oracle):
+    g = np.load(os.path.join(G, "fft.npz"))
+    for n in (256, 512, 1024, 4096, 32768):
+        assert np.array_equal(oracle.fftprocess(g[f"in_{n}"], True), g[f"fwd_{n}"])
+        assert np.array_equal(oracle.fftprocess(g[f"in_{n}"], False), g[f"inv_{n}"])
+    assert np.array_equal(oracle.bitrev_table(512), g["bitrev512"].astype(np.int32))
+    assert np.array_equal(oracle.bitrev_table(32768), g["bitrev32768"].astype(np.int32))
+    assert np.array_equal(oracle.dftprocess(g["pcm"][:512]), g["dft512"])
+    for n in (512, 1024):
+        assert np.array_equal(oracle.roundtrip(g["pcm"], n)[0], g[f"rt{n}"])
+
+
+@pytest.mark.parametrize("preset", ["ref", "bench"])
+def test_denoise_golden(oracle, preset):
+    g = np.load(os.path.join(G, "denoise.npz"))
+    for stream in (3, 17):
+        for mode, nm in ((0, "ss"), (1, "wiener")):
+            res = oracle.denoise(g[f"pcm_{stream}"], DenoiseParams.preset(preset, mode))
+            assert len(res.publish) > 0
+            assert np.array_equal(res.out, g[f"{nm}_{preset}_{stream}"])
+        assert set(np.unique(g[f"zcr_{preset}_{stream}"] - res.zcr)) <= {0, 1}
+
+
+def test_fastconv_golden(oracle):
+    g = np.load(os.path.join(G, "fastconv.npz"))
+    for ear in range(2):
+        got, _ = oracle.fastconv(g["pcm_bench"], g["hrir_bench"][ear], 512, 1, 1024)
+        assert np.array_equal(got, g[f"out_bench_ear{ear}"])
+    taps = np.zeros(7169)
+    taps[g["ref_taps_idx"]] = g["ref_taps_val"]
+    got, _ = oracle.fastconv(g["pcm_ref"], taps, 1024, 7, 8192)
+    assert np.array_equal(got, g["out_ref"])
+
+
+def test_mfcc_golden(oracle):
+    g = np.load(os.path.join(G, "mfcc.npz"))
+    for preset in ("ref", "mid"):
+        got = oracle.mfcc_program(g["pcm"], MfccParams.preset(preset))
+        assert got.shape == g[preset].shape
+        assert np.abs(got - g[preset]).max() < 1e-9
