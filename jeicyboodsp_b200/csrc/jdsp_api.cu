@@ -63,18 +63,41 @@ template <typename T> static int upload(jdsp_ctx *c, const std::vector<T> &h, T 
     return JDSP_OK;
 }
 
-// kind 0: float exp(-2*pi*j*q/n), q<n     kind 1: double same
+// Per-pass transposed Stockham twiddles (layout: jdsp::TwLayout), E = min(16, n) points per thread.
+template <typename T> static std::vector<cx<T>> pass_twiddles(int n) {
+    const int E = n < 16 ? n : 16;
+    std::vector<cx<T>> h;
+    for (int ns = 1; ns < n;) {
+        const int r = (n / ns) < E ? (n / ns) : E;
+        if (ns > 1)
+            for (int i = 1; i < r; ++i)
+                for (int k = 0; k < ns; ++k) {
+                    const double a = 2.0 * M_PI * (double)i * (double)k / ((double)ns * r);
+                    cx<T> w; w.x = (T)cos(a); w.y = (T)-sin(a);
+                    h.push_back(w);
+                }
+        ns *= r;
+    }
+    if (h.empty()) { cx<T> one; one.x = (T)1; one.y = (T)0; h.push_back(one); }
+    return h;
+}
+// kind 0: float pass twiddles for length n     kind 1: double pass twiddles
 // kind 2: float2 (cos, sin)(2*pi*k/(2n)), k<=n/2   (real-FFT post-twiddle for packed length n)
+// kind 3/4: float/double flat exp(-2*pi*j*q/n), q<n (four-step inter-stage twiddle)
 static int get_table(jdsp_ctx *c, int kind, int n, void **out) {
     auto key = std::make_pair(kind, n);
     auto it = c->tables.find(key);
     if (it != c->tables.end()) { *out = it->second; return JDSP_OK; }
     void *d = nullptr;
     if (kind == 0) {
+        cx<float> *p; TRY(upload(c, pass_twiddles<float>(n), &p)); d = p;
+    } else if (kind == 1) {
+        cx<double> *p; TRY(upload(c, pass_twiddles<double>(n), &p)); d = p;
+    } else if (kind == 3) {
         std::vector<cx<float>> h((size_t)n);
         for (int q = 0; q < n; ++q) { h[q].x = (float)cos(2.0 * M_PI * q / n); h[q].y = (float)-sin(2.0 * M_PI * q / n); }
         cx<float> *p; TRY(upload(c, h, &p)); d = p;
-    } else if (kind == 1) {
+    } else if (kind == 4) {
         std::vector<cx<double>> h((size_t)n);
         for (int q = 0; q < n; ++q) { h[q].x = cos(2.0 * M_PI * q / n); h[q].y = -sin(2.0 * M_PI * q / n); }
         cx<double> *p; TRY(upload(c, h, &p)); d = p;
@@ -202,7 +225,7 @@ static int launch_c2c_fourstep(jdsp_ctx *c, const cx<T> *in, cx<T> *out, long ba
     void *tw1, *tw2, *twN;
     TRY(get_table(c, tkind, N1, &tw1));
     TRY(get_table(c, tkind, N2, &tw2));
-    TRY(get_table(c, tkind, (int)N, &twN));
+    TRY(get_table(c, tkind + 3, (int)N, &twN));
     // chunk the batch so the intermediate stays L2-resident (<= 48 MB of the 126 MB L2)
     long chunk = (48L << 20) / (long)(N * sizeof(cx<T>));
     if (chunk < 1) chunk = 1;

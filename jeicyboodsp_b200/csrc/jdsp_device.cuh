@@ -30,16 +30,43 @@ template <> struct alignas(8) cx<float> { float x, y; };
 template <> struct alignas(16) cx<double> { double x, y; };
 
 template <typename T> JDSP_DEV cx<T> cmake(T a, T b) { cx<T> r; r.x = a; r.y = b; return r; }
-template <typename T> JDSP_DEV cx<T> cadd(cx<T> a, cx<T> b) { return cmake<T>(a.x + b.x, a.y + b.y); }
-template <typename T> JDSP_DEV cx<T> csub(cx<T> a, cx<T> b) { return cmake<T>(a.x - b.x, a.y - b.y); }
+
+// fp32 complex arithmetic rides Blackwell's packed f32x2 instructions (FADD2 / FMUL2 / FFMA2 in SASS): one
+// issue slot moves both lanes of a (re, im) pair, and ptxas folds the lane swaps and per-lane sign flips
+// of complex multiplies / +-j rotations into operand modifiers (.HI_LO, .NP).  FP pipe throughput is
+// unchanged (measured: FFMA2 issues at half the FFMA rate, profiles/microbench) but the issue slots it
+// frees go to the shared-memory and integer instructions the frame kernels are made of.
+JDSP_DEV float2 f2(cx<float> a) { return make_float2(a.x, a.y); }
+JDSP_DEV cx<float> c2(float2 a) { return cmake<float>(a.x, a.y); }
+JDSP_DEV cx<float> cadd(cx<float> a, cx<float> b) { return c2(__fadd2_rn(f2(a), f2(b))); }
+JDSP_DEV cx<float> csub(cx<float> a, cx<float> b) { return c2(__fadd2_rn(f2(a), make_float2(-b.x, -b.y))); }
+JDSP_DEV cx<double> cadd(cx<double> a, cx<double> b) { return cmake<double>(a.x + b.x, a.y + b.y); }
+JDSP_DEV cx<double> csub(cx<double> a, cx<double> b) { return cmake<double>(a.x - b.x, a.y - b.y); }
 // a * (wr + j*wi)
-template <typename T> JDSP_DEV cx<T> cmulw(cx<T> a, T wr, T wi) { return cmake<T>(a.x * wr - a.y * wi, a.x * wi + a.y * wr); }
+JDSP_DEV cx<float> cmulw(cx<float> a, float wr, float wi) {
+    const float2 t = __fmul2_rn(make_float2(a.y, a.x), make_float2(-wi, wi));
+    return c2(__ffma2_rn(f2(a), make_float2(wr, wr), t));
+}
+JDSP_DEV cx<double> cmulw(cx<double> a, double wr, double wi) { return cmake<double>(a.x * wr - a.y * wi, a.x * wi + a.y * wr); }
 // a * w, or a * conj(w) when CONJ
 template <bool CONJ, typename T> JDSP_DEV cx<T> cmul(cx<T> a, cx<T> w) {
-    return CONJ ? cmulw<T>(a, w.x, -w.y) : cmulw<T>(a, w.x, w.y);
+    return CONJ ? cmulw(a, w.x, -w.y) : cmulw(a, w.x, w.y);
 }
 // multiply by -j (forward rotation) or +j (inverse)
 template <bool INV, typename T> JDSP_DEV cx<T> crot(cx<T> a) { return INV ? cmake<T>(-a.y, a.x) : cmake<T>(a.y, -a.x); }
+// t + (-+j)*d and t - (-+j)*d without materialising the rotation
+template <bool INV> JDSP_DEV void rot_addsub(cx<float> t, cx<float> d, cx<float> &plus, cx<float> &minus) {
+    const float2 sw = make_float2(d.y, d.x);
+    const float2 sp = INV ? make_float2(-1.f, 1.f) : make_float2(1.f, -1.f);
+    const float2 sm = INV ? make_float2(1.f, -1.f) : make_float2(-1.f, 1.f);
+    plus = c2(__ffma2_rn(sw, sp, f2(t)));
+    minus = c2(__ffma2_rn(sw, sm, f2(t)));
+}
+template <bool INV> JDSP_DEV void rot_addsub(cx<double> t, cx<double> d, cx<double> &plus, cx<double> &minus) {
+    const cx<double> r = crot<INV>(d);
+    plus = cadd(t, r);
+    minus = csub(t, r);
+}
 
 // ---- in-register DFTs: natural order in, natural order out, unnormalised ----------------------
 template <bool INV, typename T> JDSP_DEV void dft2(cx<T> &a, cx<T> &b) {
@@ -47,9 +74,9 @@ template <bool INV, typename T> JDSP_DEV void dft2(cx<T> &a, cx<T> &b) {
     a = s; b = d;
 }
 template <bool INV, typename T> JDSP_DEV void dft4(cx<T> &a0, cx<T> &a1, cx<T> &a2, cx<T> &a3) {
-    const cx<T> t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = crot<INV>(csub(a1, a3));
+    const cx<T> t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), d3 = csub(a1, a3);
     a0 = cadd(t0, t2); a2 = csub(t0, t2);
-    a1 = cadd(t1, t3); a3 = csub(t1, t3);
+    rot_addsub<INV>(t1, d3, a1, a3);
 }
 // multiply by exp(-+ 2*pi*j * m/16): constants folded at compile time
 template <bool INV, int M, typename T> JDSP_DEV cx<T> cw16(cx<T> a) {
@@ -74,7 +101,7 @@ template <bool INV, int M, typename T> JDSP_DEV cx<T> cw16(cx<T> a) {
         case 14: wr = r; wi = r; break;
         default: wr = c1; wi = s1; break;  // 15
     }
-    return cmulw<T>(a, wr, INV ? -wi : wi);
+    return cmulw(a, wr, INV ? -wi : wi);
 }
 template <bool INV, typename T> JDSP_DEV void dft8(cx<T> (&a)[8]) {
     dft4<INV>(a[0], a[2], a[4], a[6]);  // even samples -> E[0..3] in a[0],a[2],a[4],a[6]
@@ -125,10 +152,28 @@ template <int SYNC> JDSP_DEV void group_sync() {
     if constexpr (SYNC == 0) __syncwarp(); else __syncthreads();
 }
 
+// Twiddle tables are stored per pass, transposed so that lanes (consecutive k) read consecutive entries:
+// pass with sub-transform size NS (> 1) and radix R owns (R-1)*NS entries, entry (i-1)*NS + k =
+// exp(-2*pi*j * i*k / (NS*R)), i = 1..R-1, k < NS.  Passes are concatenated in execution order; the whole
+// table has fewer than NC entries.  (A flat exp(-2*pi*j*q/NC) table indexed by i*k*step costs up to
+// 16-way bank conflicts in shared memory: measured, profiles/round1.)
+template <int NC, int E> struct TwLayout {
+    __host__ __device__ static constexpr int radix(int ns) { return (NC / ns) < E ? (NC / ns) : E; }
+    __host__ __device__ static constexpr int offset(int NS) {
+        int off = 0, ns = 1;
+        while (ns < NS) {
+            const int r = radix(ns);
+            if (ns > 1) off += (r - 1) * ns;
+            ns *= r;
+        }
+        return off;
+    }
+    static constexpr int total = offset(NC);
+};
+
 // One Stockham pass in registers.  reg[m] holds element (t + G*m) of the current sequence,
 // G = NC/E threads per transform.  Butterfly u (of U = E/R) uses reg[u + i*U], i < R, i.e. sequence
-// elements j + i*NC/R with j = t + G*u; k = j mod NS selects the twiddle W_{NS*R}^{i*k} taken from
-// the full-size table tw[q] = exp(-2*pi*j*q/NC).
+// elements j + i*NC/R with j = t + G*u; k = j mod NS selects the twiddle W_{NS*R}^{i*k}.
 template <typename T, int NC, int E, int R, int NS, bool INV>
 JDSP_DEV void fft_pass_compute(cx<T> (&reg)[E], int t, const cx<T> *__restrict__ tw) {
     constexpr int G = NC / E, U = E / R;
@@ -139,9 +184,10 @@ JDSP_DEV void fft_pass_compute(cx<T> (&reg)[E], int t, const cx<T> *__restrict__
         for (int i = 0; i < R; ++i) v[i] = reg[u + i * U];
         if constexpr (NS > 1) {
             const int k = (t + G * u) & (NS - 1);
-            constexpr int STEP = NC / (NS * R);
+            constexpr int TWOFF = TwLayout<NC, E>::offset(NS);
+            const cx<T> *twp = tw + TWOFF + k;
 #pragma unroll
-            for (int i = 1; i < R; ++i) v[i] = cmul<INV>(v[i], tw[i * k * STEP]);
+            for (int i = 1; i < R; ++i) v[i] = cmul<INV>(v[i], twp[(i - 1) * NS]);
         }
         dftR<R, INV>(v);
 #pragma unroll

@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(FastconvGeom<NC>::NT) fastconv_kernel(Fastconv
                                 const cf *fb = fbuf + f * PADN;
                                 cf X1, X2, Zk, Zm;
                                 untangle2x(fb[pk], fb[pm], w.x, w.y, X1, X2);
-                                const cf Y1 = cmulw<float>(X1, h1.x, h1.y), Y2 = cmulw<float>(X2, h2.x, h2.y);
+                                const cf Y1 = cmulw(X1, h1.x, h1.y), Y2 = cmulw(X2, h2.x, h2.y);
                                 retangle2x(Y1, Y2, w.x, w.y, Zk, Zm);
                                 cf *eb = ebuf + (f * 2 + ear) * PADN;
                                 if (si == 0) {

@@ -10,8 +10,19 @@ namespace jdsp {
 
 typedef cx<float> cf;
 
-JDSP_DEV float s16lo(uint32_t w) { return (float)(int)(int16_t)(w & 0xffffu); }
-JDSP_DEV float s16hi(uint32_t w) { return (float)((int)w >> 16); }
+// int16 halves of a 32-bit word -> float through the ALU-pipe I2FP (the 16-bit I2F form runs on the slow XU pipe)
+JDSP_DEV float s16lo(uint32_t w) { return __int2float_rn((int)(w << 16) >> 16); }
+JDSP_DEV float s16hi(uint32_t w) { return __int2float_rn((int)w >> 16); }
+// one MUFU.RSQ, no denormal fix-up sequence; callers clamp the argument away from 0
+JDSP_DEV float rsqrt_fast(float x) {
+#ifdef JDSP_EMUL
+    return 1.0f / sqrtf(x);
+#else
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#endif
+}
 
 // Real-input FFT bookkeeping for a length-N real frame packed as z[n] = x[2n] + j*x[2n+1], Z = DFT_M(z),
 // M = N/2.  With A = Z[k], B = Z[M-k] and W = exp(-2*pi*j*k/N) = (c, -s):
@@ -19,18 +30,22 @@ JDSP_DEV float s16hi(uint32_t w) { return (float)((int)w >> 16); }
 // untangle2x returns 2*X[k], 2*X[M-k] (callers pre-scale the frame by 1/2).  k = 0 with B = A gives the DC
 // and Nyquist bins; k = M/2 with B = A gives X[M/2] twice.
 JDSP_DEV void untangle2x(cf A, cf B, float c, float s, cf &X1, cf &X2) {
-    const float Er = A.x + B.x, Ei = A.y - B.y, Or = A.y + B.y, Oi = B.x - A.x;
-    const float Tr = c * Or + s * Oi, Ti = c * Oi - s * Or;
-    X1.x = Er + Tr; X1.y = Ei + Ti;
-    X2.x = Er - Tr; X2.y = Ti - Ei;
+    // E = A + conj B, O = (A - conj B)/j = (Ai + Bi, Br - Ar), T = W*O
+    const float2 Ev = __ffma2_rn(f2(B), make_float2(1.f, -1.f), f2(A));
+    const float2 Ov = __ffma2_rn(make_float2(A.y, A.x), make_float2(1.f, -1.f), make_float2(B.y, B.x));
+    const float2 Tv = __ffma2_rn(Ov, make_float2(c, c), __fmul2_rn(make_float2(Ov.y, Ov.x), make_float2(s, -s)));
+    X1 = c2(__fadd2_rn(Ev, Tv));
+    X2 = c2(__ffma2_rn(Tv, make_float2(-1.f, 1.f), make_float2(Ev.x, -Ev.y)));
 }
 // Inverse bookkeeping: from Y[k], Y[M-k] of a Hermitian spectrum build 2*Z'[k], 2*Z'[M-k] with
 // Z' = DFT_M of the packed real signal, so that y = IDFT_M,unnorm(2Z') / N.
 JDSP_DEV void retangle2x(cf Y1, cf Y2, float c, float s, cf &Zk, cf &Zmk) {
-    const float Sr = Y1.x + Y2.x, Si = Y1.y - Y2.y, Dr = Y1.x - Y2.x, Di = Y1.y + Y2.y;
-    const float Pr = c * Dr - s * Di, Pi = c * Di + s * Dr;
-    Zk.x = Sr - Pi; Zk.y = Si + Pr;
-    Zmk.x = Sr + Pi; Zmk.y = Pr - Si;
+    // S = Y1 + conj Y2, D = Y1 - conj Y2, P = D*conj(W), Zk = S + jP, Zmk = conj(S - jP)
+    const float2 Sv = __ffma2_rn(f2(Y2), make_float2(1.f, -1.f), f2(Y1));
+    const float2 Dv = __ffma2_rn(f2(Y2), make_float2(-1.f, 1.f), f2(Y1));
+    const float2 Pv = __ffma2_rn(Dv, make_float2(c, c), __fmul2_rn(make_float2(Dv.y, Dv.x), make_float2(-s, s)));
+    Zk = c2(__ffma2_rn(make_float2(Pv.y, Pv.x), make_float2(-1.f, 1.f), Sv));
+    Zmk = c2(__ffma2_rn(make_float2(Pv.y, Pv.x), make_float2(1.f, 1.f), make_float2(Sv.x, -Sv.y)));
 }
 
 // ================================================================================================
@@ -114,10 +129,55 @@ __global__ void __launch_bounds__(RoundtripGeom<N>::THREADS) roundtrip_kernel(Ro
 }
 
 // ================================================================================================
+// Asynchronous bulk staging (TMA 1-D bulk copy, cp.async.bulk -> UBLKCP in SASS) of frame tiles into
+// shared memory, completion tracked by an mbarrier.  One elected thread issues; every thread waits.
+// ================================================================================================
+JDSP_DEV void mbar_init(uint64_t *bar, int count) {
+#ifdef JDSP_EMUL
+    *bar = 0; (void)count;
+#else
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+}
+JDSP_DEV void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+#ifdef JDSP_EMUL
+    (void)bar; (void)bytes;
+#else
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+#endif
+}
+JDSP_DEV void bulk_g2s(void *smem_dst, const void *gsrc, unsigned bytes, uint64_t *bar) {
+#ifdef JDSP_EMUL
+    memcpy(smem_dst, gsrc, bytes); (void)bar;
+#else
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+#endif
+}
+JDSP_DEV void mbar_wait(uint64_t *bar, unsigned parity) {
+#ifdef JDSP_EMUL
+    (void)bar; (void)parity;
+#else
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(a), "r"(parity) : "memory");
+#endif
+}
+
+// ================================================================================================
 // Denoise.  One CTA walks one stream in tiles of F consecutive frames (hop H = NC, frame N = 2*NC,
 // packed-real transform length NC).  Thread groups of G = NC/16 threads own one frame each for the
 // transforms; for the per-bin stage every thread owns fixed bin pairs (k, NC-k) across ALL frames so the
 // recursive noise average and the published noise spectrum stay in registers for the whole stream.
+// The next tile's PCM is bulk-copied (TMA) into the other staging buffer while this tile is computed.
 // ================================================================================================
 struct DenoiseArgs {
     const int16_t *in; long in_pitch; long n_blocks;
@@ -127,7 +187,7 @@ struct DenoiseArgs {
     // tables (device)
     const float *win_half;        // [N]   0.5 * w[i]
     const double *win_vad;        // [H]   w[H + i] in double, for the bit-exact VAD
-    const cf *tw;                 // [NC]  exp(-2*pi*j*q/NC)
+    const cf *tw;                 // per-pass Stockham twiddles for length NC (TwLayout)
     const float2 *twr;            // [NC/2+1] (cos, sin)(2*pi*k/N)
     // per-stream state (device)
     int32_t *st_seen, *st_run, *st_pub;
@@ -146,51 +206,74 @@ struct DenoiseGeom {
     static constexpr int PADN = padded_len(NC);
     static constexpr int NSLOT = NC / 2 + 1;
     static constexpr int SPT = (NSLOT + NT - 1) / NT;
+    static constexpr int NTW = TwLayout<NC, E>::total;
+    // PCM staging: F+1 block slots per buffer, slots skewed by XPAD samples so that the two frame groups
+    // sharing a warp read different banks
+    static constexpr int XPAD = 32, XSLOT = H + XPAD, XBUF = (F + 1) * XSLOT;
     // shared memory carve-up (bytes, each region 16-byte aligned)
     static constexpr size_t OFF_FBUF = 0;
     static constexpr size_t OFF_WVAD = OFF_FBUF + (size_t)F * PADN * sizeof(cf);
     static constexpr size_t OFF_TW = OFF_WVAD + (size_t)H * sizeof(double);
-    static constexpr size_t OFF_WIN = OFF_TW + (size_t)NC * sizeof(cf);
+    static constexpr size_t OFF_WIN = OFF_TW + (((size_t)NTW * sizeof(cf) + 15) & ~(size_t)15);
     static constexpr size_t OFF_CARRY = OFF_WIN + (size_t)N * sizeof(float);
     static constexpr size_t OFF_XS = OFF_CARRY + (size_t)2 * H * sizeof(float);
-    static constexpr size_t OFF_FLAGS = OFF_XS + (size_t)(F + 1) * H * sizeof(int16_t);
-    static constexpr size_t SMEM = OFF_FLAGS + 16 * sizeof(int);
+    static constexpr size_t OFF_FLAGS = OFF_XS + (size_t)2 * XBUF * sizeof(int16_t);
+    static constexpr size_t OFF_BAR = OFF_FLAGS + 16 * sizeof(int);
+    static constexpr size_t SMEM = OFF_BAR + 2 * sizeof(uint64_t);
     static_assert(G <= 32, "frame groups must fit inside a warp");
     static_assert(PADN * 2 >= N, "the frame buffer doubles as the time-domain buffer");
+    static_assert((XSLOT * 2) % 16 == 0, "block slots must stay 16-byte aligned for bulk copies");
 };
 
 template <int NC, int F, int MODE>
 __global__ void __launch_bounds__(DenoiseGeom<NC, F>::NT) denoise_kernel(DenoiseArgs a) {
     using Geo = DenoiseGeom<NC, F>;
     constexpr int N = Geo::N, H = Geo::H, E = Geo::E, G = Geo::G, NT = Geo::NT, PADN = Geo::PADN;
-    constexpr int NSLOT = Geo::NSLOT, SPT = Geo::SPT;
+    constexpr int NSLOT = Geo::NSLOT, SPT = Geo::SPT, XSLOT = Geo::XSLOT, XBUF = Geo::XBUF;
     JDSP_DYN_SMEM(smem_raw);
     cf *fbuf = reinterpret_cast<cf *>(smem_raw + Geo::OFF_FBUF);
     double *wvad = reinterpret_cast<double *>(smem_raw + Geo::OFF_WVAD);
     cf *tw = reinterpret_cast<cf *>(smem_raw + Geo::OFF_TW);
     float *winh = reinterpret_cast<float *>(smem_raw + Geo::OFF_WIN);
     float *carry = reinterpret_cast<float *>(smem_raw + Geo::OFF_CARRY);
-    int16_t *xs = reinterpret_cast<int16_t *>(smem_raw + Geo::OFF_XS);
+    int16_t *xsb = reinterpret_cast<int16_t *>(smem_raw + Geo::OFF_XS);
     int *flags = reinterpret_cast<int *>(smem_raw + Geo::OFF_FLAGS);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + Geo::OFF_BAR);
 
     const int tid = threadIdx.x, g = tid / G, t = tid % G;
     const float inv_n = 1.0f / (float)N;
+    // kernel arguments used in the hot loop live in registers, not in the constant bank
+    const long n_blocks = a.n_blocks, skip_blocks = a.skip_blocks;
+    const int zcr_thr = a.zcr_thr, noise_frames = a.noise_frames;
+    const double energy_thr = a.energy_thr;
+    const bool want_f32 = a.out_f32 != nullptr, want_vad = a.vad != nullptr;
 
     for (int i = tid; i < H; i += NT) wvad[i] = a.win_vad[i];
-    for (int i = tid; i < NC; i += NT) tw[i] = a.tw[i];
+    for (int i = tid; i < Geo::NTW; i += NT) tw[i] = a.tw[i];
     for (int i = tid; i < N; i += NT) winh[i] = a.win_half[i];
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
+    unsigned phase0 = 0, phase1 = 0;
 
     for (long s = blockIdx.x; s < a.n_streams; s += gridDim.x) {
         // ---- load the stream's carry state ---------------------------------------------------------
         __syncthreads();
+        const int16_t *row = a.in + s * a.in_pitch;
+        int16_t *orow = a.out + s * a.out_pitch;
+        float *frow = want_f32 ? a.out_f32 + s * a.f32_pitch : nullptr;
+        uint8_t *vrow = want_vad ? a.vad + s * n_blocks : nullptr;
+        if (tid == 0) {   // bulk-stage the first tile
+            const int nf0 = n_blocks < F ? (int)n_blocks : F;
+            mbar_expect_tx(&bars[0], (unsigned)(nf0 * H * sizeof(int16_t)));
+            for (int b = 0; b < nf0; ++b) bulk_g2s(xsb + (b + 1) * XSLOT, row + (long)b * H, H * sizeof(int16_t), &bars[0]);
+        }
         const long seen0 = a.st_seen[s];
         int run = a.st_run[s];
         int pubs = a.st_pub[s];
         for (int i = tid; i < H; i += NT) {
-            xs[i] = a.st_prev[s * H + i];
+            xsb[i] = a.st_prev[s * H + i];
             carry[i] = a.st_ola[s * H + i];
         }
-        int cb = 0;
+        int cur = 0, cb = 0;
         float avg1[SPT], avg2[SPT], nss1[SPT], nss2[SPT], tc[SPT], ts[SPT];
 #pragma unroll
         for (int q = 0; q < SPT; ++q) {
@@ -207,21 +290,24 @@ __global__ void __launch_bounds__(DenoiseGeom<NC, F>::NT) denoise_kernel(Denoise
                 tc[q] = w.x; ts[q] = w.y;
             }
         }
-        const int16_t *row = a.in + s * a.in_pitch;
 
-        for (long b0 = 0; b0 < a.n_blocks; b0 += F) {
-            const int nf = (a.n_blocks - b0 < F) ? (int)(a.n_blocks - b0) : F;
-            __syncthreads();  // (A) previous tile has finished with xs[H..] and fbuf
-            {   // stage nf new blocks behind the carried previous block; zero the unused tail
-                const uint4 *src = reinterpret_cast<const uint4 *>(row + b0 * H);
-                uint4 *dst = reinterpret_cast<uint4 *>(xs + H);
-                const int nvec = nf * H / 8;
-                for (int v = tid; v < F * H / 8; v += NT) dst[v] = (v < nvec) ? src[v] : make_uint4(0, 0, 0, 0);
+        for (long b0 = 0; b0 < n_blocks; b0 += F) {
+            const int nf = (n_blocks - b0 < F) ? (int)(n_blocks - b0) : F;
+            int16_t *xs = xsb + cur * XBUF;
+            // ---- this tile's PCM has landed; the previous tile is done with the frame buffers ---------------
+            if (cur == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1u; } else { mbar_wait(&bars[1], phase1); phase1 ^= 1u; }
+            __syncthreads();  // (1)
+            if (tid == 0 && b0 + F < n_blocks) {   // stage the next tile into the other buffer while this one is processed
+                const long nb0 = b0 + F;
+                const int nfn = (n_blocks - nb0 < F) ? (int)(n_blocks - nb0) : F;
+                uint64_t *bar = &bars[cur ^ 1];
+                int16_t *xn = xsb + (cur ^ 1) * XBUF;
+                mbar_expect_tx(bar, (unsigned)(nfn * H * sizeof(int16_t)));
+                for (int b = 0; b < nfn; ++b) bulk_g2s(xn + (b + 1) * XSLOT, row + (nb0 + b) * H, H * sizeof(int16_t), bar);
             }
-            __syncthreads();  // (B)
             // ---- D1 VoiceActivityDetection on the new block of frame g (SpectralSubtraction_final.cpp:121-156)
             {
-                const uint32_t *xw = reinterpret_cast<const uint32_t *>(xs + (g + 1) * H);
+                const uint32_t *xw = reinterpret_cast<const uint32_t *>(xs + (g + 1) * XSLOT);
                 const double2 *w2 = reinterpret_cast<const double2 *>(wvad);
                 unsigned long long esum = 0ull;
                 int zc = 0;
@@ -235,7 +321,7 @@ __global__ void __launch_bounds__(DenoiseGeom<NC, F>::NT) denoise_kernel(Denoise
                     const int v0 = __double2int_rz((double)x0 * ww.x);   // short *= double  (:131)
                     const int v1 = __double2int_rz((double)x1 * ww.y);
                     esum += (unsigned long long)(unsigned)(v0 * v0) + (unsigned long long)(unsigned)(v1 * v1);  // :135
-                    zc += (v0 * x1 < 0) + (v1 * x2 < 0);                 // :138-141 windowed sample times raw next sample
+                    zc += (int)((unsigned)(v0 * x1) >> 31) + (int)((unsigned)(v1 * x2) >> 31);  // :138-141 windowed sample times raw next sample < 0
                 }
 #pragma unroll
                 for (int o = G / 2; o > 0; o >>= 1) {
@@ -243,34 +329,36 @@ __global__ void __launch_bounds__(DenoiseGeom<NC, F>::NT) denoise_kernel(Denoise
                     zc += __shfl_xor_sync(0xffffffffu, zc, o, G);
                 }
                 if (t == 0) {
-                    const double e = (double)esum / (double)N;                                   // :143
-                    const int voice = (e > a.energy_thr || (double)zc < (double)a.zcr_thr) ? 1 : 0;  // :147
+                    const double e = (double)esum / (double)N;                               // :143
+                    const int voice = (e > energy_thr || (double)zc < (double)zcr_thr) ? 1 : 0;  // :147
                     flags[g] = voice;
-                    if (a.vad && g < nf) a.vad[s * a.n_blocks + b0 + g] = (uint8_t)voice;
+                    if (want_vad && g < nf) vrow[b0 + g] = (uint8_t)voice;
                 }
             }
             // ---- frame g = [previous block | block] * window, packed real -> complex, forward transform
             cf reg[E];
             cf *buf = fbuf + g * PADN;
             {
-                const uint32_t *fw = reinterpret_cast<const uint32_t *>(xs + g * H);
+                const uint32_t *f0 = reinterpret_cast<const uint32_t *>(xs + g * XSLOT);
+                const uint32_t *f1 = reinterpret_cast<const uint32_t *>(xs + (g + 1) * XSLOT);
                 const float2 *w2 = reinterpret_cast<const float2 *>(winh);
 #pragma unroll
                 for (int m = 0; m < E; ++m) {
-                    const uint32_t wd = fw[t + G * m];
+                    const uint32_t wd = (m < E / 2) ? f0[t + G * m] : f1[t + G * (m - E / 2)];
                     const float2 w = w2[t + G * m];
-                    reg[m].x = s16lo(wd) * w.x;
-                    reg[m].y = s16hi(wd) * w.y;
+                    reg[m] = c2(__fmul2_rn(make_float2(s16lo(wd), s16hi(wd)), w));
                 }
             }
             group_fft<float, NC, E, false, 0>(reg, t, buf, tw);
             group_sync<0>();
             fft_store_regs<float, NC, E>(reg, t, buf);
-            __syncthreads();  // (C) spectra of all frames + VAD flags visible; xs no longer read
-            // carry the last valid block forward as the next tile's "previous block"
-            for (int i = tid; i < H / 2; i += NT)
-                reinterpret_cast<uint32_t *>(xs)[i] = reinterpret_cast<const uint32_t *>(xs + nf * H)[i];
-
+            __syncthreads();  // (2) spectra of all frames + VAD flags visible; this tile's PCM no longer read
+            // the last valid block becomes the next tile's "previous block" (slot 0 of the other buffer)
+            {
+                const uint32_t *src = reinterpret_cast<const uint32_t *>(xs + nf * XSLOT);
+                uint32_t *dst = reinterpret_cast<uint32_t *>(xsb + (cur ^ 1) * XBUF);
+                for (int i = tid; i < H / 2; i += NT) dst[i] = src[i];
+            }
             // ---- D5 run-length machine (main, :98-109), evaluated identically by every thread
             unsigned ctl = 0;  // per frame: bit0 update avg, bit1 halve, bit2 publish
 #pragma unroll
@@ -281,7 +369,7 @@ __global__ void __launch_bounds__(DenoiseGeom<NC, F>::NT) denoise_kernel(Denoise
                         if (run > 1) {
                             unsigned c = 1u;
                             if (run >= 3) c |= 2u;
-                            if (run == a.noise_frames) { c |= 4u; pubs++; }
+                            if (run == noise_frames) { c |= 4u; pubs++; }
                             ctl |= c << (3 * f);
                         }
                     } else {
@@ -289,7 +377,9 @@ __global__ void __launch_bounds__(DenoiseGeom<NC, F>::NT) denoise_kernel(Denoise
                     }
                 }
             }
-            // ---- per-bin stage: D2 noise estimate (:182-193) + D3/D4 gain (:237-242 / Wiener :200-213)
+            const bool first_block = (seen0 + b0 == 0);
+            // ---- per-bin stage: D2 noise estimate (:182-193) + D3/D4 gain (:237-242 / Wiener :200-213).
+            // Frames past the end of a short last tile are processed too (their ctl bits are 0, outputs masked).
 #pragma unroll
             for (int q = 0; q < SPT; ++q) {
                 const int k = tid + q * NT;
@@ -298,47 +388,41 @@ __global__ void __launch_bounds__(DenoiseGeom<NC, F>::NT) denoise_kernel(Denoise
                     const float c = tc[q], sn = ts[q];
 #pragma unroll
                     for (int f = 0; f < F; ++f) {
-                        if (f < nf) {
-                            cf *fb = fbuf + f * PADN;
-                            cf X1, X2;
-                            untangle2x(fb[pk], fb[pm], c, sn, X1, X2);
-                            const float p1 = X1.x * X1.x + X1.y * X1.y, p2 = X2.x * X2.x + X2.y * X2.y;
-                            const float r1 = rsqrtf(p1), r2 = rsqrtf(p2);
-                            const unsigned cbits = (ctl >> (3 * f)) & 7u;
-                            if (cbits & 1u) {
-                                const float m1 = p1 > 0.f ? p1 * r1 : 0.f, m2 = p2 > 0.f ? p2 * r2 : 0.f;
-                                avg1[q] += m1; avg2[q] += m2;                              // :183
-                                if (cbits & 2u) { avg1[q] *= 0.5f; avg2[q] *= 0.5f; }      // :184-186
-                                if (cbits & 4u) {                                          // :189-193
-                                    nss1[q] = (MODE == 0 ? avg1[q] : avg1[q] * avg1[q]) * inv_n;
-                                    nss2[q] = (MODE == 0 ? avg2[q] : avg2[q] * avg2[q]) * inv_n;
-                                }
+                        cf *fb = fbuf + f * PADN;
+                        cf X1, X2;
+                        untangle2x(fb[pk], fb[pm], c, sn, X1, X2);
+                        const float p1 = X1.x * X1.x + X1.y * X1.y, p2 = X2.x * X2.x + X2.y * X2.y;
+                        const float r1 = rsqrt_fast(fmaxf(p1, 1e-30f)), r2 = rsqrt_fast(fmaxf(p2, 1e-30f));
+                        const unsigned cbits = (ctl >> (3 * f)) & 7u;
+                        if (cbits) {
+                            avg1[q] += p1 * r1; avg2[q] += p2 * r2;                        // :183 (|X| = p * rsqrt(p), 0 when p = 0)
+                            if (cbits & 2u) { avg1[q] *= 0.5f; avg2[q] *= 0.5f; }          // :184-186
+                            if (cbits & 4u) {                                              // :189-193
+                                nss1[q] = (MODE == 0 ? avg1[q] : avg1[q] * avg1[q]) * inv_n;
+                                nss2[q] = (MODE == 0 ? avg2[q] : avg2[q] * avg2[q]) * inv_n;
                             }
-                            cf Y1, Y2;
-                            if (MODE == 0) {  // amp = |X| - ns, no floor (:238); Y = amp * e^{j angle X}
-                                const float g1 = fmaf(-nss1[q], r1, inv_n), g2 = fmaf(-nss2[q], r2, inv_n);
-                                Y1.x = g1 * X1.x; Y1.y = g1 * X1.y;
-                                Y2.x = g2 * X2.x; Y2.y = g2 * X2.y;
-                                if (!(p1 > 0.f)) { Y1.x = -nss1[q]; Y1.y = 0.f; }  // |X| = 0: atan2(0,0) = 0 (appendix C-7)
-                                if (!(p2 > 0.f)) { Y2.x = -nss2[q]; Y2.y = 0.f; }
-                            } else {          // amp = |X| * (1 - min(ns^2/|X|^2, 1))  (WienerFilter_final.cpp:204-208)
-                                const float g1 = inv_n - fminf(nss1[q] * (r1 * r1), inv_n);
-                                const float g2 = inv_n - fminf(nss2[q] * (r2 * r2), inv_n);
-                                Y1.x = g1 * X1.x; Y1.y = g1 * X1.y;
-                                Y2.x = g2 * X2.x; Y2.y = g2 * X2.y;
-                                if (!(p1 > 0.f)) { Y1.x = 0.f; Y1.y = 0.f; }
-                                if (!(p2 > 0.f)) { Y2.x = 0.f; Y2.y = 0.f; }
-                            }
-                            if (seen0 + b0 + f == 0) { Y1.x = Y1.y = Y2.x = Y2.y = 0.f; }  // first block only primes the keep buffer (:211-216)
-                            cf Zk, Zm;
-                            retangle2x(Y1, Y2, c, sn, Zk, Zm);
-                            fb[pk] = Zk;
-                            fb[pm] = Zm;
                         }
+                        float g1, g2;
+                        if (MODE == 0) {  // amp = |X| - ns, no floor (:238); Y = amp * e^{j angle X}
+                            g1 = fmaf(-nss1[q], r1, inv_n); g2 = fmaf(-nss2[q], r2, inv_n);
+                        } else {          // amp = |X| * (1 - min(ns^2/|X|^2, 1))  (WienerFilter_final.cpp:204-208)
+                            g1 = inv_n - fminf(nss1[q] * (r1 * r1), inv_n);
+                            g2 = inv_n - fminf(nss2[q] * (r2 * r2), inv_n);
+                        }
+                        if (f == 0 && first_block) { g1 = 0.f; g2 = 0.f; }  // the very first block only primes the keep buffer (:211-216)
+                        cf Y1 = c2(__fmul2_rn(f2(X1), make_float2(g1, g1))), Y2 = c2(__fmul2_rn(f2(X2), make_float2(g2, g2)));
+                        if (MODE == 0) {  // |X| = 0: atan2(0,0) = 0, so the reference emits (-ns, 0) (appendix C-7); X = 0 made Y = 0 above
+                            if (p1 == 0.f && !(f == 0 && first_block)) Y1.x = -nss1[q];
+                            if (p2 == 0.f && !(f == 0 && first_block)) Y2.x = -nss2[q];
+                        }
+                        cf Zk, Zm;
+                        retangle2x(Y1, Y2, c, sn, Zk, Zm);
+                        fb[pk] = Zk;
+                        fb[pm] = Zm;
                     }
                 }
             }
-            __syncthreads();  // (D)
+            __syncthreads();  // (3)
             // ---- inverse transform of frame g, time samples into the frame buffer (as floats)
             fft_load_regs<float, NC, E>(reg, t, buf);
             group_sync<0>();
@@ -346,47 +430,40 @@ __global__ void __launch_bounds__(DenoiseGeom<NC, F>::NT) denoise_kernel(Denoise
             group_sync<0>();
 #pragma unroll
             for (int m = 0; m < E; ++m) buf[t + G * m] = reg[m];  // y[2n], y[2n+1] at natural positions (unpadded)
-            __syncthreads();  // (E)
-            // ---- overlap-add (:248-256), (short) cast (:252), coalesced 16-byte stores
+            __syncthreads();  // (4)
+            // ---- overlap-add (:248-256), (short) cast (:252), coalesced stores, 4 samples per thread and step
             {
                 const float *cprev = carry + cb * H;
                 float *cnext = carry + (cb ^ 1) * H;
-                for (int it = tid; it < nf * (H / 8); it += NT) {
-                    const int f = it / (H / 8), n0 = (it % (H / 8)) * 8;
+                for (int it = tid; it < nf * (H / 4); it += NT) {
+                    const int f = it / (H / 4), n0 = (it % (H / 4)) * 4;
                     const float *yc = reinterpret_cast<const float *>(fbuf + f * PADN) + n0;
                     const float *yp = (f == 0) ? (cprev + n0) : (reinterpret_cast<const float *>(fbuf + (f - 1) * PADN) + H + n0);
-                    const float4 c0 = *reinterpret_cast<const float4 *>(yc), c1 = *reinterpret_cast<const float4 *>(yc + 4);
-                    const float4 p0 = *reinterpret_cast<const float4 *>(yp), p1 = *reinterpret_cast<const float4 *>(yp + 4);
-                    float o[8] = {c0.x + p0.x, c0.y + p0.y, c0.z + p0.z, c0.w + p0.w,
-                                  c1.x + p1.x, c1.y + p1.y, c1.z + p1.z, c1.w + p1.w};
-                    const long blk = b0 + f - a.skip_blocks;
+                    const float4 c0 = *reinterpret_cast<const float4 *>(yc), p0 = *reinterpret_cast<const float4 *>(yp);
+                    const float o0 = c0.x + p0.x, o1 = c0.y + p0.y, o2 = c0.z + p0.z, o3 = c0.w + p0.w;
+                    const long blk = b0 + f - skip_blocks;
                     if (blk >= 0) {
-                        uint32_t pk[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            pk[i] = ((uint32_t)(uint16_t)trunc16(o[2 * i])) | ((uint32_t)(uint16_t)trunc16(o[2 * i + 1]) << 16);
-                        *reinterpret_cast<uint4 *>(a.out + s * a.out_pitch + blk * H + n0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                        if (a.out_f32) {
-                            float *of = a.out_f32 + s * a.f32_pitch + blk * H + n0;
-                            *reinterpret_cast<float4 *>(of) = make_float4(o[0], o[1], o[2], o[3]);
-                            *reinterpret_cast<float4 *>(of + 4) = make_float4(o[4], o[5], o[6], o[7]);
-                        }
+                        const uint32_t lo = ((uint32_t)(uint16_t)trunc16(o0)) | ((uint32_t)(uint16_t)trunc16(o1) << 16);
+                        const uint32_t hi = ((uint32_t)(uint16_t)trunc16(o2)) | ((uint32_t)(uint16_t)trunc16(o3) << 16);
+                        *reinterpret_cast<uint2 *>(orow + blk * H + n0) = make_uint2(lo, hi);
+                        if (want_f32) *reinterpret_cast<float4 *>(frow + blk * H + n0) = make_float4(o0, o1, o2, o3);
                     }
                 }
                 const float *ylast = reinterpret_cast<const float *>(fbuf + (nf - 1) * PADN) + H;
                 for (int i = tid; i < H; i += NT) cnext[i] = ylast[i];
                 cb ^= 1;
             }
+            cur ^= 1;
         }
         // ---- store the stream's carry state ------------------------------------------------------
         __syncthreads();
         if (tid == 0) {
-            a.st_seen[s] = (int32_t)(seen0 + a.n_blocks);
+            a.st_seen[s] = (int32_t)(seen0 + n_blocks);
             a.st_run[s] = run;
             a.st_pub[s] = pubs;
         }
         for (int i = tid; i < H; i += NT) {
-            a.st_prev[s * H + i] = xs[i];
+            a.st_prev[s * H + i] = xsb[cur * XBUF + i];
             a.st_ola[s * H + i] = carry[cb * H + i];
         }
 #pragma unroll

@@ -141,6 +141,9 @@ static inline double __int2double_rn(int x) { return (double)x; }
 static inline float __int_as_float(int x) { float f; memcpy(&f, &x, 4); return f; }
 static inline int __float_as_int(float f) { int x; memcpy(&x, &f, 4); return x; }
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+static inline float2 __fadd2_rn(float2 a, float2 b) { return {a.x + b.x, a.y + b.y}; }
+static inline float2 __fmul2_rn(float2 a, float2 b) { return {a.x * b.x, a.y * b.y}; }
+static inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return {fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline unsigned __brev(unsigned x) {
