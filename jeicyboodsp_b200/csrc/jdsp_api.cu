@@ -648,10 +648,15 @@ int jdsp_fastconv_state_create(jdsp_ctx *c, const jdsp_fastconv_params *p, long 
     REQUIRE(p->n_ears == 1 || p->n_ears == 2, "n_ears must be 1 or 2");
     REQUIRE(p->n_fft == (p->history_blocks + 1) * p->block, "n_fft must equal (history_blocks+1)*block");
     REQUIRE(p->n_taps >= 1 && p->n_taps == p->history_blocks * p->block + 1, "n_taps must equal history_blocks*block + 1 (the reference keeps y[n_taps-1 ..])");
-    REQUIRE(p->block % 2 == 0, "block must be even");
+    REQUIRE(p->block % 8 == 0, "block must be a multiple of 8 samples");
     const int NC = p->n_fft / 2;
-    if (NC != 256 && NC != 512 && NC != 1024 && NC != 2048 && NC != 4096)
-        return fail(JDSP_ERR_UNSUPPORTED, "fast-conv supports n_fft 512..8192");
+    {
+        const int key = NC * 16 + p->history_blocks;
+        const int ok[] = {256 * 16 + 1, 512 * 16 + 1, 1024 * 16 + 1, 2048 * 16 + 1, 1024 * 16 + 3, 2048 * 16 + 3, 2048 * 16 + 7, 4096 * 16 + 7};
+        bool found = false;
+        for (int k : ok) found = found || (k == key);
+        if (!found) return fail(JDSP_ERR_UNSUPPORTED, "fast-conv supports history_blocks 1 (n_fft 512..4096), 3 (2048, 4096) or 7 (4096, 8192)");
+    }
     CU(cudaSetDevice(c->device));
     jdsp_fastconv_state *st = new jdsp_fastconv_state();
     st->p = *p;
@@ -679,13 +684,11 @@ int jdsp_fastconv_state_create(jdsp_ctx *c, const jdsp_fastconv_params *p, long 
 }
 }  // extern "C"
 
-template <int NC> static int launch_fastconv(jdsp_ctx *c, const FastconvArgs &a) {
-    using Geo = FastconvGeom<NC>;
-    auto kfn = fastconv_kernel<NC>;
-    const size_t smem = Geo::smem(a.B, a.q);
-    if (smem > 227 * 1024) return fail(JDSP_ERR_UNSUPPORTED, "fast-conv tile does not fit shared memory");
-    TRY(opt_in_smem(kfn, smem));
-    JDSP_LAUNCH_PTR(kfn, dim3(grid_for(c, a.n_scenes, 32)), dim3(Geo::NT), smem, c->stream, a);
+template <int NC, int Q> static int launch_fastconv(jdsp_ctx *c, const FastconvArgs &a) {
+    using Geo = FastconvGeom<NC, Q>;
+    auto kfn = fastconv_kernel<NC, Q>;
+    TRY(opt_in_smem(kfn, Geo::SMEM));
+    JDSP_LAUNCH_PTR(kfn, dim3(grid_for(c, a.n_scenes, 32)), dim3(Geo::NT), Geo::SMEM, c->stream, a);
     return launch_check(c);
 }
 static int fastconv_run(jdsp_ctx *c, jdsp_fastconv_state *st, int sources_per_scene, const int16_t *d_in, long in_pitch, long n_blocks,
@@ -699,7 +702,8 @@ static int fastconv_run(jdsp_ctx *c, jdsp_fastconv_state *st, int sources_per_sc
     if (n_out_blocks) *n_out_blocks = emitted;
     if (n_blocks == 0) return JDSP_OK;
     REQUIRE(emitted == 0 || d_out, "d_out is null");
-    REQUIRE(in_pitch % 2 == 0 && out_pitch % 2 == 0, "pitches must be even");
+    REQUIRE(in_pitch % 8 == 0 && out_pitch % 4 == 0 && f32_pitch % 4 == 0, "row pitches must keep rows 16-byte (in) / 8-byte (out) aligned");
+    REQUIRE((((uintptr_t)d_in) & 15) == 0 && (((uintptr_t)d_out) & 7) == 0 && (((uintptr_t)d_out_f32) & 15) == 0, "buffers must be 16-byte aligned");
     CU(cudaSetDevice(c->device));
     const int NC = p.n_fft / 2;
     void *tw, *twr;
@@ -711,12 +715,17 @@ static int fastconv_run(jdsp_ctx *c, jdsp_fastconv_state *st, int sources_per_sc
     a.st_hist = st->d_hist; a.n_scenes = st->n_sources / sources_per_scene; a.sources_per_scene = sources_per_scene;
     a.B = p.block; a.q = p.history_blocks; a.n_ears = p.n_ears; a.shared_filter = p.shared_filter; a.seen0 = st->seen;
     int rc;
-    switch (NC) {
-        case 256: rc = launch_fastconv<256>(c, a); break;
-        case 512: rc = launch_fastconv<512>(c, a); break;
-        case 1024: rc = launch_fastconv<1024>(c, a); break;
-        case 2048: rc = launch_fastconv<2048>(c, a); break;
-        default: rc = launch_fastconv<4096>(c, a); break;
+    const int key = NC * 16 + p.history_blocks;
+    switch (key) {
+        case 256 * 16 + 1: rc = launch_fastconv<256, 1>(c, a); break;
+        case 512 * 16 + 1: rc = launch_fastconv<512, 1>(c, a); break;    // bench preset
+        case 1024 * 16 + 1: rc = launch_fastconv<1024, 1>(c, a); break;
+        case 2048 * 16 + 1: rc = launch_fastconv<2048, 1>(c, a); break;
+        case 1024 * 16 + 3: rc = launch_fastconv<1024, 3>(c, a); break;
+        case 2048 * 16 + 3: rc = launch_fastconv<2048, 3>(c, a); break;
+        case 2048 * 16 + 7: rc = launch_fastconv<2048, 7>(c, a); break;
+        case 4096 * 16 + 7: rc = launch_fastconv<4096, 7>(c, a); break;  // the reference program's literal constants
+        default: return fail(JDSP_ERR_UNSUPPORTED, "fast-conv supports history_blocks 1 (n_fft 512..4096), 3 (2048, 4096) or 7 (4096, 8192)");
     }
     if (rc == JDSP_OK) st->seen += n_blocks;
     return rc;
@@ -804,8 +813,8 @@ int jdsp_mfcc_plan_destroy(jdsp_ctx *c, jdsp_mfcc_plan *pl) {
 int jdsp_mfcc_plan_create(jdsp_ctx *c, const jdsp_mfcc_params *p, jdsp_mfcc_plan **out) {
     REQUIRE(c && p && out, "null argument");
     if (p->n_fft != 512 && p->n_fft != 1024) return fail(JDSP_ERR_UNSUPPORTED, "MFCC supports n_fft 512 or 1024");
-    REQUIRE(p->frame_len >= 2 && p->frame_len <= p->n_fft && p->frame_len % 2 == 0, "frame_len must be even and <= n_fft");
-    REQUIRE(p->hop >= 2 && p->hop % 2 == 0, "hop must be even");
+    REQUIRE(p->frame_len >= 8 && p->frame_len <= p->n_fft && p->frame_len % 8 == 0, "frame_len must be a multiple of 8 and <= n_fft");
+    REQUIRE(p->hop >= 8 && p->hop % 8 == 0, "hop must be a multiple of 8 samples (16-byte bulk copies)");
     REQUIRE(p->n_mel >= 1 && p->n_mel <= 64 && p->n_cep >= 1 && p->n_cep <= 32, "n_mel <= 64 and n_cep <= 32");
     CU(cudaSetDevice(c->device));
     jdsp_mfcc_plan *pl = new jdsp_mfcc_plan();
@@ -874,7 +883,7 @@ int jdsp_mfcc_frames_i16_dev(jdsp_ctx *c, jdsp_mfcc_plan *pl, const int16_t *d_i
     if (n_frames) *n_frames = nf;
     if (nf == 0 || n_utts == 0) return JDSP_OK;
     REQUIRE(d_feat, "d_feat is null");
-    REQUIRE(in_pitch % 2 == 0, "in_pitch must be even");
+    REQUIRE(in_pitch % 8 == 0 && (((uintptr_t)d_in) & 15) == 0, "utterance rows must be 16-byte aligned (in_pitch % 8 == 0)");
     REQUIRE(feat_pitch >= nf * p.n_cep, "feat_pitch too small");
     CU(cudaSetDevice(c->device));
     const int NC = p.n_fft / 2;
@@ -910,7 +919,7 @@ int jdsp_mfcc_program_i16(jdsp_ctx *c, const jdsp_mfcc_params *p, const int16_t 
     if (e != cudaSuccess) rc = fail(JDSP_ERR_CUDA, std::string("mfcc_program setup: ") + cudaGetErrorString(e));
     if (rc == JDSP_OK) rc = apply_stale_tail(c, d_in + H, total, 1, n_samples, (int)B);
     long nf = 0;
-    if (rc == JDSP_OK) rc = jdsp_mfcc_frames_i16_dev(c, pl, d_in, total + (total & 1), 1, total, d_feat, (long)hfeat.size(), &nf);
+    if (rc == JDSP_OK) rc = jdsp_mfcc_frames_i16_dev(c, pl, d_in, (total + 7) & ~7L, 1, total, d_feat, (long)hfeat.size(), &nf);
     if (rc == JDSP_OK) {
         e = cudaMemcpyAsync(hfeat.data(), d_feat, hfeat.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);

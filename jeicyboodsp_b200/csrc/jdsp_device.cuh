@@ -194,6 +194,8 @@ JDSP_DEV void fft_pass_compute(cx<T> (&reg)[E], int t, const cx<T> *__restrict__
         for (int i = 0; i < R; ++i) reg[u + i * U] = v[i];
     }
 }
+// Padded addresses with compile-time strides: for a stride S that is a multiple of 16,
+// pad16(b + i*S) == pad16(b) + i*(S + S/16); for b a multiple of 16 and i < 16, pad16(b + i) == pad16(b) + i.
 // scatter the outputs of a non-final pass to their Stockham positions (padded)
 template <typename T, int NC, int E, int R, int NS>
 JDSP_DEV void fft_pass_store(const cx<T> (&reg)[E], int t, cx<T> *buf) {
@@ -202,19 +204,41 @@ JDSP_DEV void fft_pass_store(const cx<T> (&reg)[E], int t, cx<T> *buf) {
     for (int u = 0; u < U; ++u) {
         const int j = t + G * u, k = j & (NS - 1);
         const int base = (j - k) * R + k;
+        if constexpr (NS % 16 == 0) {
+            cx<T> *p = buf + pad16(base);
 #pragma unroll
-        for (int i = 0; i < R; ++i) buf[pad16(base + i * NS)] = reg[u + i * U];
+            for (int i = 0; i < R; ++i) p[i * (NS + NS / 16)] = reg[u + i * U];
+        } else if constexpr (NS == 1 && R == 16) {
+            cx<T> *p = buf + pad16(base);  // base = 16*j
+#pragma unroll
+            for (int i = 0; i < R; ++i) p[i] = reg[u + i * U];
+        } else {
+#pragma unroll
+            for (int i = 0; i < R; ++i) buf[pad16(base + i * NS)] = reg[u + i * U];
+        }
     }
 }
 template <typename T, int NC, int E> JDSP_DEV void fft_load_regs(cx<T> (&reg)[E], int t, const cx<T> *buf) {
     constexpr int G = NC / E;
+    if constexpr (G % 16 == 0) {
+        const cx<T> *p = buf + pad16(t);
 #pragma unroll
-    for (int m = 0; m < E; ++m) reg[m] = buf[pad16(t + G * m)];
+        for (int m = 0; m < E; ++m) reg[m] = p[m * (G + G / 16)];
+    } else {
+#pragma unroll
+        for (int m = 0; m < E; ++m) reg[m] = buf[pad16(t + G * m)];
+    }
 }
 template <typename T, int NC, int E> JDSP_DEV void fft_store_regs(const cx<T> (&reg)[E], int t, cx<T> *buf) {
     constexpr int G = NC / E;
+    if constexpr (G % 16 == 0) {
+        cx<T> *p = buf + pad16(t);
 #pragma unroll
-    for (int m = 0; m < E; ++m) buf[pad16(t + G * m)] = reg[m];
+        for (int m = 0; m < E; ++m) p[m * (G + G / 16)] = reg[m];
+    } else {
+#pragma unroll
+        for (int m = 0; m < E; ++m) buf[pad16(t + G * m)] = reg[m];
+    }
 }
 
 // Whole transform.  In: reg[m] = x[t + G*m].  Out: reg[m] = X[t + G*m] (natural order).
@@ -237,5 +261,15 @@ JDSP_DEV void group_fft(cx<T> (&reg)[E], int t, cx<T> *buf, const cx<T> *__restr
 // ---- small numeric helpers ---------------------------------------------------------------------------
 // (short)(double) of the reference: truncate toward zero, keep the low 16 bits
 JDSP_DEV int16_t trunc16(float v) { return (int16_t)__float2int_rz(v); }
+// single-instruction approximations (MUFU); callers keep arguments away from 0 / denormals where it matters
+JDSP_DEV float sqrt_fast(float x) {
+#ifdef JDSP_EMUL
+    return sqrtf(x);
+#else
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#endif
+}
 
 }  // namespace jdsp

@@ -23,83 +23,87 @@ struct FastconvArgs {
     long seen0;                            // blocks consumed before this call (same for every source)
 };
 
-template <int NC>
+template <int NC, int Q>
 struct FastconvGeom {
-    static constexpr int N = 2 * NC, E = 16, G = NC / E;
+    static constexpr int N = 2 * NC, E = 16, G = NC / E, B = N / (Q + 1);
     static constexpr int SYNC = G > 32 ? 1 : 0;
     static constexpr int NT = G > 128 ? G : 128;
     static constexpr int F = NT / G;                 // overlap-save windows per tile
     static constexpr int PADN = padded_len(NC);
     static constexpr int NSLOT = NC / 2 + 1;
     static constexpr int SPT = (NSLOT + NT - 1) / NT;
+    static constexpr int XLEN = (Q + F) * B;         // samples per staging buffer: Q history blocks + F new
     // fbuf [F][PADN] cf (spectrum of the current source), ebuf [F][2][PADN] cf (per-ear accumulators / time buffers)
     static constexpr size_t OFF_FBUF = 0;
     static constexpr size_t OFF_EBUF = OFF_FBUF + (size_t)F * PADN * sizeof(cf);
     static constexpr size_t OFF_XS = OFF_EBUF + (size_t)F * 2 * PADN * sizeof(cf);
-    static size_t smem(int B, int q) { return OFF_XS + 2 * (size_t)(q + F) * B * sizeof(int16_t); }
+    static constexpr size_t SMEM = OFF_XS + 2 * (size_t)XLEN * sizeof(int16_t);
+    static_assert(B * (Q + 1) == N && B % 8 == 0, "block must divide the window into Q+1 pieces of 8k samples");
 };
 
-template <int NC>
-__global__ void __launch_bounds__(FastconvGeom<NC>::NT) fastconv_kernel(FastconvArgs a) {
-    using Geo = FastconvGeom<NC>;
+template <int NC, int Q>
+__global__ void __launch_bounds__(FastconvGeom<NC, Q>::NT) fastconv_kernel(FastconvArgs a) {
+    using Geo = FastconvGeom<NC, Q>;
     constexpr int N = Geo::N, E = Geo::E, G = Geo::G, NT = Geo::NT, F = Geo::F, PADN = Geo::PADN, SYNC = Geo::SYNC;
-    constexpr int NSLOT = Geo::NSLOT, SPT = Geo::SPT;
+    constexpr int NSLOT = Geo::NSLOT, SPT = Geo::SPT, B = Geo::B, XLEN = Geo::XLEN, BV = B / 8;
     JDSP_DYN_SMEM(smem_raw);
     cf *fbuf = reinterpret_cast<cf *>(smem_raw + Geo::OFF_FBUF);
     cf *ebuf = reinterpret_cast<cf *>(smem_raw + Geo::OFF_EBUF);
     int16_t *xs_base = reinterpret_cast<int16_t *>(smem_raw + Geo::OFF_XS);
-    const int B = a.B, q = a.q, S = a.sources_per_scene, NE = a.n_ears;
-    const int xs_len = (q + F) * B;
+    const int S = a.sources_per_scene, NE = a.n_ears;
     const int tid = threadIdx.x, g = tid / G, t = tid % G;
-    const long skip = a.seen0 < q ? q - a.seen0 : 0;  // blocks of this call that emit nothing (:118-123)
+    const long n_blocks = a.n_blocks, seen0 = a.seen0, in_pitch = a.in_pitch, out_pitch = a.out_pitch, f32_pitch = a.f32_pitch;
+    const long skip = seen0 < Q ? Q - seen0 : 0;  // blocks of this call that emit nothing (:118-123)
+    const bool want_f32 = a.out_f32 != nullptr;
+    const cf *tw = a.tw;
+    // post-twiddles of this thread's bin pairs never change: registers
+    float tc[SPT], ts[SPT];
+#pragma unroll
+    for (int qq = 0; qq < SPT; ++qq) {
+        const int k = tid + qq * NT;
+        const float2 w = (k < NSLOT) ? a.twr[k] : make_float2(1.f, 0.f);
+        tc[qq] = w.x; ts[qq] = w.y;
+    }
 
     for (long scene = blockIdx.x; scene < a.n_scenes; scene += gridDim.x) {
         int cur = 0;
-        for (long b0 = 0; b0 < a.n_blocks; b0 += F) {
-            const int nf = (a.n_blocks - b0 < F) ? (int)(a.n_blocks - b0) : F;
+        for (long b0 = 0; b0 < n_blocks; b0 += F) {
+            const int nf = (n_blocks - b0 < F) ? (int)(n_blocks - b0) : F;
             for (int si = 0; si < S; ++si) {
                 const long src = scene * S + si;
-                const int16_t *row = a.in + src * a.in_pitch;
-                int16_t *xs = xs_base + (size_t)((S == 1) ? (cur ^ 1) : 0) * xs_len;
-                const int16_t *xold = xs_base + (size_t)cur * xs_len;
+                const int16_t *row = a.in + src * in_pitch;
+                int16_t *xs = xs_base + ((S == 1) ? (cur ^ 1) : 0) * XLEN;
+                const int16_t *xold = xs_base + cur * XLEN;
                 __syncthreads();  // (A)
-                // ---- history (q blocks) ------------------------------------------------------------------
-                for (int i = tid; i < q * B; i += NT) {
-                    int16_t v;
-                    if (S == 1 && b0 > 0) {
-                        v = xold[F * B + i];                       // last q blocks of the previous tile's window
-                    } else {
-                        const long gi = b0 * B - (long)q * B + i;  // sample index within this call
-                        v = gi >= 0 ? row[gi] : a.st_hist[src * (long)q * B + (q * B + gi)];
-                        // blocks the reference never filled count as zeros (appendix C-4)
-                        const long gblk = a.seen0 + (gi >= 0 ? gi / B : -((-gi + B - 1) / B));
-                        if (gblk < q) v = 0;
+                // ---- window history (Q blocks) then the new blocks, 16 bytes per thread and step.  Blocks the
+                // reference never filled (global index < Q) count as zeros (appendix C-4).
+#pragma unroll 2
+                for (int v = tid; v < (Q + F) * BV; v += NT) {
+                    const int blk = v / BV, off = (v % BV) * 8;   // blk 0..Q-1 history, Q.. new
+                    const long gb = b0 + blk - Q;                 // block index within this call (negative: before it)
+                    uint4 val = make_uint4(0, 0, 0, 0);
+                    if (blk < Q && S == 1 && b0 > 0) {
+                        val = *reinterpret_cast<const uint4 *>(xold + (F + blk) * B + off);
+                    } else if (blk - Q < nf && seen0 + gb >= Q) {
+                        val = gb >= 0 ? *reinterpret_cast<const uint4 *>(row + gb * B + off)
+                                      : *reinterpret_cast<const uint4 *>(a.st_hist + src * (long)(Q * B) + (Q + gb) * B + off);
                     }
-                    xs[i] = v;
-                }
-                // ---- new blocks ------------------------------------------------------------------------------
-                for (int i = tid; i < F * B; i += NT) {
-                    int16_t v = 0;
-                    if (i < nf * B) {
-                        v = row[b0 * B + i];
-                        if (a.seen0 + b0 + i / B < q) v = 0;
-                    }
-                    xs[q * B + i] = v;
+                    *reinterpret_cast<uint4 *>(xs + blk * B + off) = val;
                 }
                 __syncthreads();  // (B)
                 // ---- forward transform of window g: xs[g*B .. g*B+N) ------------------------------------------
                 cf reg[E];
                 cf *buf = fbuf + g * PADN;
                 {
-                    const uint32_t *fw = reinterpret_cast<const uint32_t *>(xs + g * B);
+                    const uint32_t *fw = reinterpret_cast<const uint32_t *>(xs + g * B) + t;
 #pragma unroll
                     for (int m = 0; m < E; ++m) {
-                        const uint32_t wd = fw[t + G * m];
+                        const uint32_t wd = fw[G * m];
                         reg[m].x = s16lo(wd);
                         reg[m].y = s16hi(wd);
                     }
                 }
-                group_fft<float, NC, E, false, SYNC>(reg, t, buf, a.tw);
+                group_fft<float, NC, E, false, SYNC>(reg, t, buf, tw);
                 group_sync<SYNC>();
                 fft_store_regs<float, NC, E>(reg, t, buf);
                 __syncthreads();  // (C)
@@ -110,15 +114,17 @@ __global__ void __launch_bounds__(FastconvGeom<NC>::NT) fastconv_kernel(Fastconv
                     const int k = tid + qq * NT;
                     if (k < NSLOT) {
                         const int pk = pad16(k), pm = pad16((NC - k) & (NC - 1));
-                        const float2 w = a.twr[k];
+                        const float wc = tc[qq], wsn = ts[qq];
                         for (int ear = 0; ear < NE; ++ear) {
-                            const cf h1 = hsrc[ear * (NC + 1) + k], h2 = hsrc[ear * (NC + 1) + NC - k];
-                            for (int f = 0; f < nf; ++f) {
+                            const cf h1 = c2(__ldg(reinterpret_cast<const float2 *>(hsrc + ear * (NC + 1) + k)));
+                            const cf h2 = c2(__ldg(reinterpret_cast<const float2 *>(hsrc + ear * (NC + 1) + NC - k)));
+#pragma unroll
+                            for (int f = 0; f < F; ++f) {
                                 const cf *fb = fbuf + f * PADN;
                                 cf X1, X2, Zk, Zm;
-                                untangle2x(fb[pk], fb[pm], w.x, w.y, X1, X2);
+                                untangle2x(fb[pk], fb[pm], wc, wsn, X1, X2);
                                 const cf Y1 = cmulw(X1, h1.x, h1.y), Y2 = cmulw(X2, h2.x, h2.y);
-                                retangle2x(Y1, Y2, w.x, w.y, Zk, Zm);
+                                retangle2x(Y1, Y2, wc, wsn, Zk, Zm);
                                 cf *eb = ebuf + (f * 2 + ear) * PADN;
                                 if (si == 0) {
                                     eb[pk] = Zk; eb[pm] = Zm;
@@ -131,10 +137,10 @@ __global__ void __launch_bounds__(FastconvGeom<NC>::NT) fastconv_kernel(Fastconv
                         }
                     }
                 }
-                // keep this source's newest q blocks for the next call
-                if (b0 + F >= a.n_blocks) {
-                    __syncthreads();
-                    for (int i = tid; i < q * B; i += NT) a.st_hist[src * (long)q * B + i] = xs[nf * B + i];
+                // keep this source's newest Q blocks for the next call
+                if (b0 + F >= n_blocks) {
+                    for (int v = tid; v < Q * BV; v += NT)
+                        *reinterpret_cast<uint4 *>(a.st_hist + src * (long)(Q * B) + v * 8) = *reinterpret_cast<const uint4 *>(xs + nf * B + v * 8);
                 }
             }
             if (S == 1) cur ^= 1;
@@ -145,26 +151,25 @@ __global__ void __launch_bounds__(FastconvGeom<NC>::NT) fastconv_kernel(Fastconv
                 cf *buf = ebuf + (g * 2 + ear) * PADN;
                 fft_load_regs<float, NC, E>(reg, t, buf);
                 group_sync<SYNC>();
-                group_fft<float, NC, E, true, SYNC>(reg, t, buf, a.tw);
+                group_fft<float, NC, E, true, SYNC>(reg, t, buf, tw);
                 group_sync<SYNC>();
 #pragma unroll
                 for (int m = 0; m < E; ++m) buf[t + G * m] = reg[m];
             }
             __syncthreads();  // (E)
             for (int ear = 0; ear < NE; ++ear) {
-                for (int it = tid; it < nf * (B / 2); it += NT) {
-                    const int f = it / (B / 2), n = (it % (B / 2)) * 2;
-                    const float *y = reinterpret_cast<const float *>(ebuf + (f * 2 + ear) * PADN) + (N - B) + n;
+                int16_t *orow = a.out + (scene * NE + ear) * out_pitch;
+                float *frow = want_f32 ? a.out_f32 + (scene * NE + ear) * f32_pitch : nullptr;
+#pragma unroll 2
+                for (int it = tid; it < F * (B / 4); it += NT) {
+                    const int f = it / (B / 4), n = (it % (B / 4)) * 4;
                     const long blk = b0 + f - skip;
-                    if (blk >= 0) {
-                        const float v0 = y[0], v1 = y[1];
-                        const uint32_t pk = ((uint32_t)(uint16_t)trunc16(v0)) | ((uint32_t)(uint16_t)trunc16(v1) << 16);
-                        const long o = (scene * NE + ear) * a.out_pitch + blk * B + n;
-                        *reinterpret_cast<uint32_t *>(a.out + o) = pk;
-                        if (a.out_f32) {
-                            float *of = a.out_f32 + (scene * NE + ear) * a.f32_pitch + blk * B + n;
-                            of[0] = v0; of[1] = v1;
-                        }
+                    if (f < nf && blk >= 0) {
+                        const float4 y = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(ebuf + (f * 2 + ear) * PADN) + (N - B) + n);
+                        const uint32_t lo = ((uint32_t)(uint16_t)trunc16(y.x)) | ((uint32_t)(uint16_t)trunc16(y.y) << 16);
+                        const uint32_t hi = ((uint32_t)(uint16_t)trunc16(y.z)) | ((uint32_t)(uint16_t)trunc16(y.w) << 16);
+                        *reinterpret_cast<uint2 *>(orow + blk * B + n) = make_uint2(lo, hi);
+                        if (want_f32) *reinterpret_cast<float4 *>(frow + blk * B + n) = y;
                     }
                 }
             }
@@ -194,104 +199,145 @@ struct MfccGeom {
     static constexpr int NSLOT = NC / 2 + 1;
     static constexpr int SPT = (NSLOT + NT - 1) / NT;
     static constexpr int MAXMEL = 64, MAXCEP = 32;
+    static constexpr int MAGP = F + 1;               // |X| is stored [bin][frame] with an odd pitch: conflict-free both ways
     static constexpr size_t OFF_FBUF = 0;
     static constexpr size_t OFF_MAG = OFF_FBUF + (size_t)F * PADN * sizeof(cf);
-    static constexpr size_t OFF_MEL = OFF_MAG + (size_t)F * NC * sizeof(float);
-    static constexpr size_t OFF_XS = OFF_MEL + (size_t)F * MAXMEL * sizeof(float);
-    static size_t smem(int frame_len, int hop) { return OFF_XS + (((size_t)((F - 1) * hop + frame_len) * 2 + 4 + 15) & ~(size_t)15); }
+    static constexpr size_t OFF_MEL = OFF_MAG + (((size_t)NC * MAGP * sizeof(float)) + 15 & ~(size_t)15);
+    static constexpr size_t OFF_MELW = OFF_MEL + (size_t)F * MAXMEL * sizeof(float);       // [NC] filterbank weights
+    static constexpr size_t OFF_DCT = OFF_MELW + (size_t)NC * sizeof(float);              // [MAXMEL][MAXCEP] (cepstrum index fastest)
+    static constexpr size_t OFF_START = OFF_DCT + (size_t)MAXCEP * MAXMEL * sizeof(float); // [MAXMEL+2]
+    static constexpr size_t OFF_WINH = OFF_START + (size_t)(MAXMEL + 8) * sizeof(int);     // [N] half window (zero past frame_len)
+    static constexpr size_t OFF_BAR = OFF_WINH + (size_t)N * sizeof(float);
+    static constexpr size_t OFF_XS = OFF_BAR + 16;
+    __host__ __device__ static size_t span_bytes(int frame_len, int hop) { return ((size_t)((F - 1) * hop + frame_len) * 2 + 15) & ~(size_t)15; }
+    static size_t smem(int frame_len, int hop) { return OFF_XS + 2 * span_bytes(frame_len, hop); }
     static_assert(G <= 32, "frame groups must fit inside a warp");
 };
 
+// Tiles of F consecutive frames of one utterance; frames are independent, so the grid walks (utterance, tile)
+// pairs.  The PCM span of the NEXT tile is bulk-copied (TMA) into the other staging buffer during this tile.
 template <int NC>
 __global__ void __launch_bounds__(MfccGeom<NC>::NT) mfcc_kernel(MfccArgs a) {
     using Geo = MfccGeom<NC>;
     constexpr int E = Geo::E, G = Geo::G, NT = Geo::NT, F = Geo::F, PADN = Geo::PADN, NSLOT = Geo::NSLOT, SPT = Geo::SPT;
+    constexpr int MAGP = Geo::MAGP, MAXMEL = Geo::MAXMEL, MAXCEP = Geo::MAXCEP;
     JDSP_DYN_SMEM(smem_raw);
     cf *fbuf = reinterpret_cast<cf *>(smem_raw + Geo::OFF_FBUF);
     float *mag = reinterpret_cast<float *>(smem_raw + Geo::OFF_MAG);
     float *mel = reinterpret_cast<float *>(smem_raw + Geo::OFF_MEL);
-    int16_t *xs = reinterpret_cast<int16_t *>(smem_raw + Geo::OFF_XS);
+    float *melw = reinterpret_cast<float *>(smem_raw + Geo::OFF_MELW);
+    float *dct = reinterpret_cast<float *>(smem_raw + Geo::OFF_DCT);
+    int *mstart = reinterpret_cast<int *>(smem_raw + Geo::OFF_START);
+    float *winh = reinterpret_cast<float *>(smem_raw + Geo::OFF_WINH);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + Geo::OFF_BAR);
     const int tid = threadIdx.x, g = tid / G, t = tid % G;
     const int W = a.frame_len, hop = a.hop, C = a.n_mel, NCEP = a.n_cep;
-    const long tiles_per_utt = (a.n_frames + F - 1) / F;
+    const float preemph = a.preemph;
+    const long n_frames = a.n_frames, in_pitch = a.in_pitch, feat_pitch = a.feat_pitch;
+    const cf *tw = a.tw;
+    const size_t span_b = Geo::span_bytes(W, hop);
+    int16_t *xsb = reinterpret_cast<int16_t *>(smem_raw + Geo::OFF_XS);
+    for (int i = tid; i < NC; i += NT) melw[i] = a.mel_w[i];
+    for (int i = tid; i < NCEP * C; i += NT) dct[(i % C) * MAXCEP + (i / C)] = a.dct[i];
+    for (int i = tid; i < C + 2; i += NT) mstart[i] = a.mel_start[i];
+    for (int i = tid; i < 2 * NC; i += NT) winh[i] = i < W ? a.win_half[i] : 0.f;
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
+    float tc[SPT], ts[SPT];
+#pragma unroll
+    for (int qq = 0; qq < SPT; ++qq) {
+        const int k = tid + qq * NT;
+        const float2 w = (k < NSLOT) ? a.twr[k] : make_float2(1.f, 0.f);
+        tc[qq] = w.x; ts[qq] = w.y;
+    }
+    const long tiles_per_utt = (n_frames + F - 1) / F;
     const long n_tiles = a.n_utts * tiles_per_utt;
-    const int span = (F - 1) * hop + W;  // samples covered by a full tile (even: hop and frame_len are even)
+    // bytes of PCM a tile needs: (nf-1)*hop + frame_len samples (hop and frame_len are multiples of 8 samples)
+    auto issue = [&](long tile, int bufi) {
+        const long u = tile / tiles_per_utt, t0 = (tile % tiles_per_utt) * F;
+        const int nf = (n_frames - t0 < F) ? (int)(n_frames - t0) : F;
+        const unsigned bytes = (unsigned)(((nf - 1) * hop + W) * 2);
+        mbar_expect_tx(&bars[bufi], bytes);
+        bulk_g2s(reinterpret_cast<unsigned char *>(xsb) + bufi * span_b, a.in + u * in_pitch + t0 * hop, bytes, &bars[bufi]);
+    };
+    __syncthreads();
+    if (tid == 0 && (long)blockIdx.x < n_tiles) issue(blockIdx.x, 0);
+    unsigned phase0 = 0, phase1 = 0;
+    int cur = 0;
 
     for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long u = tile / tiles_per_utt;
         const long t0 = (tile % tiles_per_utt) * F;
-        const int nf = (a.n_frames - t0 < F) ? (int)(a.n_frames - t0) : F;
-        const int16_t *src = a.in + u * a.in_pitch + t0 * hop;
-        const long avail = a.n_samples - t0 * hop;
-        __syncthreads();  // (A)
-        {
-            const uint32_t *s32 = reinterpret_cast<const uint32_t *>(src);
-            uint32_t *x32 = reinterpret_cast<uint32_t *>(xs);
-            for (int w = tid; w < span / 2; w += NT) x32[w] = (2L * w + 1 < avail) ? s32[w] : 0u;
-        }
-        __syncthreads();  // (B)
+        const int nf = (n_frames - t0 < F) ? (int)(n_frames - t0) : F;
+        const int16_t *xs = reinterpret_cast<const int16_t *>(reinterpret_cast<unsigned char *>(xsb) + cur * span_b);
+        if (cur == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1u; } else { mbar_wait(&bars[1], phase1); phase1 ^= 1u; }
+        __syncthreads();  // (A) PCM landed; previous tile finished with fbuf / mag / mel
+        if (tid == 0 && tile + gridDim.x < n_tiles) issue(tile + gridDim.x, cur ^ 1);
         // ---- pre-emphasis (:208-210), window (:212-214), packed real transform of frame g ------------
         cf reg[E];
         cf *buf = fbuf + g * PADN;
         {
-            const uint32_t *fw = reinterpret_cast<const uint32_t *>(xs + g * hop);
-            const float2 *w2 = reinterpret_cast<const float2 *>(a.win_half);
+            const uint32_t *fw = reinterpret_cast<const uint32_t *>(xs + g * hop) + t;
+            const float2 *w2 = reinterpret_cast<const float2 *>(winh) + t;
 #pragma unroll
             for (int m = 0; m < E; ++m) {
-                const int n = t + G * m;  // packed index: samples 2n, 2n+1
+                const int n = t + G * m;  // packed index: samples 2n, 2n+1; the window table is 0 past frame_len
                 float vx = 0.f, vy = 0.f;
-                if (2 * n + 1 < W) {
-                    const uint32_t wd = fw[n];
+                if (2 * n + 1 < W && g < nf) {
+                    const uint32_t wd = fw[G * m];
                     const float f0 = s16lo(wd), f1 = s16hi(wd);
-                    const float fm = n > 0 ? s16hi(fw[n - 1]) : 0.f;
-                    const float2 w = w2[n];
-                    vx = n > 0 ? (f0 - a.preemph * fm) * w.x : 0.f;  // element 0 is never pre-emphasised: stays 0
-                    vy = (f1 - a.preemph * f0) * w.y;
+                    const float fm = n > 0 ? s16hi(fw[G * m - 1]) : 0.f;
+                    const float2 w = w2[G * m];
+                    vx = n > 0 ? (f0 - preemph * fm) * w.x : 0.f;  // element 0 is never pre-emphasised: stays 0
+                    vy = (f1 - preemph * f0) * w.y;
                 }
                 reg[m].x = vx; reg[m].y = vy;
             }
         }
-        group_fft<float, NC, E, false, 0>(reg, t, buf, a.tw);
+        group_fft<float, NC, E, false, 0>(reg, t, buf, tw);
         group_sync<0>();
         fft_store_regs<float, NC, E>(reg, t, buf);
         __syncthreads();  // (C)
-        // ---- |X[i]|, i < n_fft/2 (:218-220) --------------------------------------------------------------
+        // ---- |X[i]|, i < n_fft/2 (:218-220), stored [bin][frame] ------------------------------------------
 #pragma unroll
         for (int qq = 0; qq < SPT; ++qq) {
             const int k = tid + qq * NT;
             if (k < NSLOT) {
                 const int pk = pad16(k), pm = pad16((NC - k) & (NC - 1));
-                const float2 w = a.twr[k];
-                for (int f = 0; f < nf; ++f) {
+                const float wc = tc[qq], wsn = ts[qq];
+                const bool second = (k > 0 && k < NC - k);
+#pragma unroll
+                for (int f = 0; f < F; ++f) {
                     const cf *fb = fbuf + f * PADN;
                     cf X1, X2;
-                    untangle2x(fb[pk], fb[pm], w.x, w.y, X1, X2);
-                    mag[f * NC + k] = sqrtf(X1.x * X1.x + X1.y * X1.y);
-                    if (k > 0 && k < NC - k) mag[f * NC + NC - k] = sqrtf(X2.x * X2.x + X2.y * X2.y);
+                    untangle2x(fb[pk], fb[pm], wc, wsn, X1, X2);
+                    if (k < NC) mag[k * MAGP + f] = sqrt_fast(X1.x * X1.x + X1.y * X1.y);
+                    if (second) mag[(NC - k) * MAGP + f] = sqrt_fast(X2.x * X2.x + X2.y * X2.y);
                 }
             }
         }
         __syncthreads();  // (D)
-        // ---- M3 MelFilterBank (:154-174): channel c collects (1-w)*a over bins with index c and w*a over index c+1
-        for (int it = tid; it < nf * C; it += NT) {
-            const int f = it / C, c = it % C;
-            const int i0 = a.mel_start[c], i1 = a.mel_start[c + 1], i2 = a.mel_start[c + 2];
-            const float *mg = mag + f * NC;
+        // ---- M3 MelFilterBank (:154-174): channel c collects (1-w)*a over bins with index c and w*a over index c+1.
+        // Item = (channel, frame) with the frame fastest, so the lanes of a warp walk 4 neighbouring channels of
+        // similar width and read consecutive floats.
+        for (int it = tid; it < C * F; it += NT) {
+            const int c = it / F, f = it % F;
+            const int i0 = mstart[c], i1 = mstart[c + 1], i2 = mstart[c + 2];
+            const float *mg = mag + f;
             float acc = 0.f;
-            for (int i = i0; i < i1; ++i) acc += (1.f - a.mel_w[i]) * mg[i];
-            for (int i = i1; i < i2; ++i) acc += a.mel_w[i] * mg[i];
-            mel[f * Geo::MAXMEL + c] = logf(acc);  // :170-172
+            for (int i = i0; i < i1; ++i) acc = fmaf(1.f - melw[i], mg[i * MAGP], acc);
+            for (int i = i1; i < i2; ++i) acc = fmaf(melw[i], mg[i * MAGP], acc);
+            mel[f * MAXMEL + c] = logf(acc);  // :170-172
         }
         __syncthreads();  // (E)
         // ---- M4 DCT (:176-183) with M5 lifter (:185-192) folded into the table ------------------------------
         for (int it = tid; it < nf * NCEP; it += NT) {
             const int f = it / NCEP, i = it % NCEP;
-            const float *ml = mel + f * Geo::MAXMEL;
-            const float *d = a.dct + i * C;
+            const float *ml = mel + f * MAXMEL;
             float acc = 0.f;
-            for (int c = 0; c < C; ++c) acc += d[c] * ml[c];
-            a.feat[u * a.feat_pitch + (t0 + f) * NCEP + i] = acc;
+            for (int c = 0; c < C; ++c) acc = fmaf(dct[c * MAXCEP + i], ml[c], acc);
+            a.feat[u * feat_pitch + (t0 + f) * NCEP + i] = acc;
         }
+        cur ^= 1;
     }
 }
 
