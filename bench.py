@@ -172,6 +172,10 @@ def main_gpu(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # libraries (NCCL prints its version banner) must not pollute stdout: the contract is ONE JSON line
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: libjdsp has no CPU fallback")
     torch.cuda.set_device(local)
@@ -315,7 +319,9 @@ def main_gpu(args):
                          "note": "4 B/sample (int16 in + int16 out); the kernel is fp32-issue/shared-memory bound, see DESIGN.md"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "parity": parity,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
     for st in states.values():
         st.close()
     if world > 1:
