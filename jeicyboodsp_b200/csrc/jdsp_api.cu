@@ -6,6 +6,7 @@
 
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -220,21 +221,23 @@ static int launch_c2c_small(jdsp_ctx *c, const cx<T> *in, cx<T> *out, long batch
 }
 template <typename T, int N1, int N2, bool INV>
 static int launch_c2c_fourstep(jdsp_ctx *c, const cx<T> *in, cx<T> *out, long batch, int tkind) {
-    constexpr int CT = 16, RT = 16;
+    constexpr int CT = sizeof(T) == 4 ? 32 : 16, RT = sizeof(T) == 4 ? 32 : 16;
     const long N = (long)N1 * N2;
     void *tw1, *tw2, *twN;
     TRY(get_table(c, tkind, N1, &tw1));
     TRY(get_table(c, tkind, N2, &tw2));
     TRY(get_table(c, tkind + 3, (int)N, &twN));
-    // chunk the batch so the intermediate stays L2-resident (<= 48 MB of the 126 MB L2)
-    long chunk = (48L << 20) / (long)(N * sizeof(cx<T>));
+    // chunk the batch so the scratch buffer stays bounded (measured: launch count matters more than L2 residency here)
+    long chunk_mb = 512;
+    if (const char *e = getenv("JDSP_FOURSTEP_CHUNK_MB")) chunk_mb = atol(e) > 0 ? atol(e) : chunk_mb;  // tuning knob
+    long chunk = (chunk_mb << 20) / (long)(N * sizeof(cx<T>));
     if (chunk < 1) chunk = 1;
     if (chunk > batch) chunk = batch;
     TRY(ensure_scratch(c, (size_t)chunk * N * sizeof(cx<T>)));
     cx<T> *tmp = (cx<T> *)c->scratch;
     auto ka = fft_cols_kernel<T, N1, CT, INV>;
     auto kb = fft_rows_kernel<T, N2, RT, INV>;
-    const size_t sa = (size_t)CT * FftGeom<N1>::PADN * sizeof(cx<T>), sb = (size_t)RT * FftGeom<N2>::PADN * sizeof(cx<T>);
+    const size_t sa = (size_t)CT * (FftGeom<N1>::PADN + 1) * sizeof(cx<T>), sb = (size_t)RT * (FftGeom<N2>::PADN + 1) * sizeof(cx<T>);
     TRY(opt_in_smem(ka, sa));
     TRY(opt_in_smem(kb, sb));
     for (long b0 = 0; b0 < batch; b0 += chunk) {
@@ -258,7 +261,7 @@ static int fft_dispatch(jdsp_ctx *c, const cx<T> *in, cx<T> *out, int n, long ba
 #define SMALL(NN) case NN: return launch_c2c_small<T, NN, INV>(c, in, out, batch, t);
         SMALL(2) SMALL(4) SMALL(8) SMALL(16) SMALL(32) SMALL(64) SMALL(128) SMALL(256) SMALL(512) SMALL(1024) SMALL(2048) SMALL(4096) SMALL(8192)
 #undef SMALL
-        case 16384: return launch_c2c_fourstep<T, 128, 128, INV>(c, in, out, batch, tkind);
+        case 16384: return launch_c2c_fourstep<T, 64, 256, INV>(c, in, out, batch, tkind);
         case 32768: return launch_c2c_fourstep<T, 128, 256, INV>(c, in, out, batch, tkind);
         case 65536: return launch_c2c_fourstep<T, 256, 256, INV>(c, in, out, batch, tkind);
         default: return fail(JDSP_ERR_UNSUPPORTED, "FFT length must be a power of two in [2, 65536]");

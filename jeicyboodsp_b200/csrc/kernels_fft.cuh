@@ -18,6 +18,8 @@ template <int N> struct FftGeom {
     // transforms per CTA: aim for 256 threads
     static constexpr int FPB = G >= 256 ? 1 : 256 / G;
     static constexpr int THREADS = FPB * G;
+    // ask ptxas for enough resident CTAs that loads, exchanges and stores of different transforms overlap
+    static constexpr int MINB = THREADS >= 512 ? 2 : (THREADS >= 256 ? 3 : 1);
 };
 
 // Cooperative, coalesced copy between a contiguous global tile of FPB transforms and the padded
@@ -41,111 +43,161 @@ JDSP_DEV void tile_store(const cx<T> *sm, cx<T> *__restrict__ g, long valid_elem
     }
 }
 
+// N >= 256: every thread moves its 16 points straight between global memory and registers (lanes of a group
+// touch consecutive complex values, so the accesses are coalesced); shared memory only carries the inter-pass
+// exchanges.  N < 256: groups are narrower than 16 lanes, so tiles are staged through shared memory instead.
 template <typename T, int N, bool INV>
-__global__ void __launch_bounds__(FftGeom<N>::THREADS)
+__global__ void __launch_bounds__(FftGeom<N>::THREADS, sizeof(T) == 4 ? FftGeom<N>::MINB : 1)
 fft_c2c_kernel(const cx<T> *__restrict__ in, cx<T> *__restrict__ out, long batch, const cx<T> *__restrict__ tw, T scale) {
     using Geo = FftGeom<N>;
     constexpr int E = Geo::E, G = Geo::G, FPB = Geo::FPB, PADN = Geo::PADN;
     JDSP_DYN_SMEM(smem_raw);
     cx<T> *sm = reinterpret_cast<cx<T> *>(smem_raw);
     const int grp = threadIdx.x / G, t = threadIdx.x % G;
-    for (long tile = blockIdx.x; tile * FPB < batch; tile += gridDim.x) {
-        const long first = tile * FPB;
-        const long valid = (batch - first < FPB ? batch - first : FPB) * (long)N;
-        __syncthreads();  // previous tile fully stored before its buffers are refilled
-        tile_load<T, N, FPB, Geo::THREADS>(sm, in + first * N, valid);
-        __syncthreads();
-        cx<T> reg[E];
-        cx<T> *buf = sm + grp * PADN;
-        fft_load_regs<T, N, E>(reg, t, buf);
-        if constexpr (G > 1) group_sync<Geo::SYNC>();  // all loads done before pass stores
-        group_fft<T, N, E, INV, Geo::SYNC>(reg, t, buf, tw);
-        if constexpr (G > 1 && N > E) group_sync<Geo::SYNC>();  // last-pass loads done before natural-order store
-        fft_store_regs<T, N, E>(reg, t, buf);
-        __syncthreads();
-        tile_store<T, N, FPB, Geo::THREADS>(sm, out + first * N, valid, scale);
+    cx<T> *buf = sm + grp * PADN;
+    if constexpr (G >= 16) {
+        for (long tile = blockIdx.x; tile * FPB < batch; tile += gridDim.x) {
+            const long f = tile * FPB + grp;
+            const bool live = f < batch;
+            cx<T> reg[E];
+            if (live) {
+                const cx<T> *src = in + f * N + t;
+#pragma unroll
+                for (int m = 0; m < E; ++m) reg[m] = src[G * m];
+            } else {
+#pragma unroll
+                for (int m = 0; m < E; ++m) reg[m] = cmake<T>((T)0, (T)0);
+            }
+            group_sync<Geo::SYNC>();  // the previous transform of this group has finished reading the exchange buffer
+            group_fft<T, N, E, INV, Geo::SYNC>(reg, t, buf, tw);
+            if (live) {
+                cx<T> *dst = out + f * N + t;
+#pragma unroll
+                for (int m = 0; m < E; ++m) { reg[m].x *= scale; reg[m].y *= scale; dst[G * m] = reg[m]; }
+            }
+        }
+    } else {
+        for (long tile = blockIdx.x; tile * FPB < batch; tile += gridDim.x) {
+            const long first = tile * FPB;
+            const long valid = (batch - first < FPB ? batch - first : FPB) * (long)N;
+            __syncthreads();  // previous tile fully stored before its buffers are refilled
+            tile_load<T, N, FPB, Geo::THREADS>(sm, in + first * N, valid);
+            __syncthreads();
+            cx<T> reg[E];
+            fft_load_regs<T, N, E>(reg, t, buf);
+            if constexpr (G > 1) group_sync<Geo::SYNC>();  // all loads done before pass stores
+            group_fft<T, N, E, INV, Geo::SYNC>(reg, t, buf, tw);
+            if constexpr (G > 1 && N > E) group_sync<Geo::SYNC>();  // last-pass loads done before natural-order store
+            fft_store_regs<T, N, E>(reg, t, buf);
+            __syncthreads();
+            tile_store<T, N, FPB, Geo::THREADS>(sm, out + first * N, valid, scale);
+        }
     }
 }
 
 // ---- four-step for N = N1 * N2 (both handled by one thread group each) -----------------------------------
 // Step A: for CT adjacent columns n2, DFT over n1 (stride N2), multiply by W_N^(n2*k1), write row-major [k1][n2].
+// Global accesses are CT*sizeof(cx) contiguous bytes per row; all loads of a tile are issued before the first
+// shared-memory store so a CTA keeps its whole tile in flight.
 template <typename T, int N1, int CT, bool INV>
-__global__ void __launch_bounds__(CT * FftGeom<N1>::G)
+__global__ void __launch_bounds__(CT * FftGeom<N1>::G, sizeof(T) == 4 ? (CT * FftGeom<N1>::G >= 512 ? 2 : 3) : 1)
 fft_cols_kernel(const cx<T> *__restrict__ in, cx<T> *__restrict__ tmp, int N2, long n_fft, const cx<T> *__restrict__ tw1,
                 const cx<T> *__restrict__ twN) {
     using Geo = FftGeom<N1>;
-    constexpr int E = Geo::E, G = Geo::G, PADN = Geo::PADN, THREADS = CT * G;
+    constexpr int E = Geo::E, G = Geo::G, THREADS = CT * G;
+    constexpr int PADN = Geo::PADN + 1;      // odd pitch (in 8-byte units mod 16): the transposing accesses across columns stay conflict-free
+    constexpr int PER = N1 * CT / THREADS;   // elements each thread stages = E
     static_assert(G <= 32, "column transforms must fit a warp-level group");
+    static_assert(PER == E && THREADS % CT == 0, "staging assumes one element per (row-slab, column)");
     JDSP_DYN_SMEM(smem_raw);
     cx<T> *sm = reinterpret_cast<cx<T> *>(smem_raw);
     const int tiles_per_fft = N2 / CT;
     const long n_tiles = n_fft * tiles_per_fft;
     const long N = (long)N1 * N2;
+    const int sc = threadIdx.x % CT, sr = threadIdx.x / CT;   // staging role: column sc, rows sr + (THREADS/CT)*i
+    const int c = threadIdx.x / G, t = threadIdx.x % G;       // transform role: column c, lane t
     for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long f = tile / tiles_per_fft;
         const int c0 = (int)(tile % tiles_per_fft) * CT;
-        const cx<T> *src = in + f * N + c0;
-        cx<T> *dst = tmp + f * N + c0;
+        const cx<T> *src = in + f * N + c0 + sc;
+        cx<T> *dst = tmp + f * N + c0 + sc;
+        cx<T> st[PER];
+#pragma unroll
+        for (int i = 0; i < PER; ++i) st[i] = src[(long)(sr + (THREADS / CT) * i) * N2];
+        // twiddles W_N^((c0+c)*k1), k1 = t + G*m: three exact table reads, the rest by short products (depth <= 4)
+        const long col = c0 + c;
+        const cx<T> wa = twN[col * t], b1 = twN[col * G], b4 = twN[col * (4 * G)];
+        __syncthreads();  // previous tile has been written out of shared memory
+#pragma unroll
+        for (int i = 0; i < PER; ++i) sm[sc * PADN + pad16(sr + (THREADS / CT) * i)] = st[i];
         __syncthreads();
-        for (int e = threadIdx.x; e < N1 * CT; e += THREADS) {
-            const int n1 = e / CT, c = e % CT;
-            sm[c * PADN + pad16(n1)] = src[(long)n1 * N2 + c];
-        }
-        __syncthreads();
-        const int c = threadIdx.x / G, t = threadIdx.x % G;
         cx<T> reg[E];
         cx<T> *buf = sm + c * PADN;
         fft_load_regs<T, N1, E>(reg, t, buf);
         group_sync<0>();
         group_fft<T, N1, E, INV, 0>(reg, t, buf, tw1);
         group_sync<0>();
+        {
+            const cx<T> b2 = cmul<false>(b1, b1), b3 = cmul<false>(b2, b1);
+            const cx<T> b8 = cmul<false>(b4, b4), b12 = cmul<false>(b8, b4);
+            cx<T> aj[4];
+            aj[0] = wa; aj[1] = cmul<false>(wa, b4); aj[2] = cmul<false>(wa, b8); aj[3] = cmul<false>(wa, b12);
 #pragma unroll
-        for (int m = 0; m < E; ++m) {
-            const int k1 = t + G * m;
-            const cx<T> w = twN[(long)(c0 + c) * k1];  // < N since c0+c < N2 and k1 < N1
-            buf[pad16(k1)] = cmul<INV>(reg[m], w);
+            for (int m = 0; m < E; ++m) {
+                const int r = m & 3;
+                cx<T> w = aj[m >> 2];
+                if (r == 1) w = cmul<false>(w, b1);
+                if (r == 2) w = cmul<false>(w, b2);
+                if (r == 3) w = cmul<false>(w, b3);
+                reg[m] = cmul<INV>(reg[m], w);
+            }
         }
+        fft_store_regs<T, N1, E>(reg, t, buf);
         __syncthreads();
-        for (int e = threadIdx.x; e < N1 * CT; e += THREADS) {
-            const int k1 = e / CT, cc = e % CT;
-            dst[(long)k1 * N2 + cc] = sm[cc * PADN + pad16(k1)];
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int k1 = sr + (THREADS / CT) * i;
+            dst[(long)k1 * N2] = sm[sc * PADN + pad16(k1)];
         }
     }
 }
-// Step B: for RT adjacent rows k1 of [k1][n2], DFT over n2, write X[k1 + N1*k2].
+// Step B: for RT adjacent rows k1 of [k1][n2], DFT over n2 (contiguous rows: straight into registers), then a
+// shared-memory transpose so that X[k1 + N1*k2] leaves in runs of RT consecutive values.
 template <typename T, int N2, int RT, bool INV>
-__global__ void __launch_bounds__(RT * FftGeom<N2>::G)
+__global__ void __launch_bounds__(RT * FftGeom<N2>::G, sizeof(T) == 4 ? (RT * FftGeom<N2>::G >= 512 ? 2 : 3) : 1)
 fft_rows_kernel(const cx<T> *__restrict__ tmp, cx<T> *__restrict__ out, int N1, long n_fft, const cx<T> *__restrict__ tw2, T scale) {
     using Geo = FftGeom<N2>;
-    constexpr int E = Geo::E, G = Geo::G, PADN = Geo::PADN, THREADS = RT * G;
-    static_assert(G <= 32, "row transforms must fit a warp-level group");
+    constexpr int E = Geo::E, G = Geo::G, THREADS = RT * G;
+    constexpr int PADN = Geo::PADN + 1;      // odd pitch, see fft_cols_kernel
+    constexpr int PER = N2 * RT / THREADS;
+    static_assert(G <= 32 && G >= 16, "row transforms must fit a warp-level group of at least 16 lanes");
     JDSP_DYN_SMEM(smem_raw);
     cx<T> *sm = reinterpret_cast<cx<T> *>(smem_raw);
     const int tiles_per_fft = N1 / RT;
     const long n_tiles = n_fft * tiles_per_fft;
     const long N = (long)N1 * N2;
+    const int r = threadIdx.x / G, t = threadIdx.x % G;       // transform role
+    const int orr = threadIdx.x % RT, ok = threadIdx.x / RT;  // output role: row orr, k2 = ok + (THREADS/RT)*i
     for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long f = tile / tiles_per_fft;
         const int r0 = (int)(tile % tiles_per_fft) * RT;
-        const cx<T> *src = tmp + f * N + (long)r0 * N2;
-        cx<T> *dst = out + f * N + r0;
-        __syncthreads();
-        for (int e = threadIdx.x; e < N2 * RT; e += THREADS) sm[(e / N2) * PADN + pad16(e % N2)] = src[e];
-        __syncthreads();
-        const int r = threadIdx.x / G, t = threadIdx.x % G;
+        const cx<T> *src = tmp + f * N + (long)(r0 + r) * N2 + t;
+        cx<T> *dst = out + f * N + r0 + orr;
         cx<T> reg[E];
+#pragma unroll
+        for (int m = 0; m < E; ++m) reg[m] = src[G * m];
         cx<T> *buf = sm + r * PADN;
-        fft_load_regs<T, N2, E>(reg, t, buf);
-        group_sync<0>();
+        __syncthreads();  // previous tile has been written out of shared memory
         group_fft<T, N2, E, INV, 0>(reg, t, buf, tw2);
         group_sync<0>();
         fft_store_regs<T, N2, E>(reg, t, buf);
         __syncthreads();
-        for (int e = threadIdx.x; e < N2 * RT; e += THREADS) {
-            const int k2 = e / RT, rr = e % RT;
-            cx<T> v = sm[rr * PADN + pad16(k2)];
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int k2 = ok + (THREADS / RT) * i;
+            cx<T> v = sm[orr * PADN + pad16(k2)];
             v.x *= scale; v.y *= scale;
-            dst[(long)k2 * N1 + rr] = v;
+            dst[(long)k2 * N1] = v;
         }
     }
 }
