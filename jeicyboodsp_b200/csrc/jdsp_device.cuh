@@ -258,6 +258,26 @@ JDSP_DEV void group_fft(cx<T> (&reg)[E], int t, cx<T> *buf, const cx<T> *__restr
     }
 }
 
+// Two-pass transform (NC = E*R2, e.g. 256 = 16*16) whose second-pass twiddles W_NC^(i*t), i = 1..R2-1, are thread
+// constants kept in registers by the caller: they cost no shared-memory wavefronts (the flat loads are ~11 % of
+// the denoise kernel's shared-memory traffic).
+template <typename T, int NC, int E> JDSP_DEV void load_pass2_twiddles(cx<T> (&twv)[E - 1], int t, const cx<T> *__restrict__ tw) {
+    static_assert(NC == E * E, "register twiddles are for the E x E two-pass case");
+#pragma unroll
+    for (int i = 1; i < E; ++i) twv[i - 1] = tw[TwLayout<NC, E>::offset(E) + (i - 1) * E + t];
+}
+template <typename T, int NC, int E, bool INV, int SYNC>
+JDSP_DEV void group_fft_regtw(cx<T> (&reg)[E], int t, cx<T> *buf, const cx<T> (&twv)[E - 1]) {
+    static_assert(NC == E * E, "register twiddles are for the E x E two-pass case");
+    dftR<E, INV>(reg);
+    fft_pass_store<T, NC, E, E, 1>(reg, t, buf);
+    group_sync<SYNC>();
+    fft_load_regs<T, NC, E>(reg, t, buf);
+#pragma unroll
+    for (int i = 1; i < E; ++i) reg[i] = cmul<INV>(reg[i], twv[i - 1]);
+    dftR<E, INV>(reg);
+}
+
 // ---- small numeric helpers ---------------------------------------------------------------------------
 // (short)(double) of the reference: truncate toward zero, keep the low 16 bits
 JDSP_DEV int16_t trunc16(float v) { return (int16_t)__float2int_rz(v); }

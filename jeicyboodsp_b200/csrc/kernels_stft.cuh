@@ -226,7 +226,7 @@ struct DenoiseGeom {
 };
 
 template <int NC, int F, int MODE>
-__global__ void __launch_bounds__(DenoiseGeom<NC, F>::NT) denoise_kernel(DenoiseArgs a) {
+__global__ void __launch_bounds__(DenoiseGeom<NC, F>::NT, NC == 256 ? 6 : 3) denoise_kernel(DenoiseArgs a) {
     using Geo = DenoiseGeom<NC, F>;
     constexpr int N = Geo::N, H = Geo::H, E = Geo::E, G = Geo::G, NT = Geo::NT, PADN = Geo::PADN;
     constexpr int NSLOT = Geo::NSLOT, SPT = Geo::SPT, XSLOT = Geo::XSLOT, XBUF = Geo::XBUF;
@@ -248,6 +248,11 @@ __global__ void __launch_bounds__(DenoiseGeom<NC, F>::NT) denoise_kernel(Denoise
     const double energy_thr = a.energy_thr;
     const bool want_f32 = a.out_f32 != nullptr, want_vad = a.vad != nullptr;
 
+    // Register-resident second-pass twiddles (NC == 256) were measured: 30 fewer shared-memory wavefronts per frame but
+    // 56 -> 80+ registers and no speed-up (the kernel is latency-bound at 24 warps/SM, not wavefront-bound): off.
+    constexpr bool REGTW = false;
+    cf twv[E - 1];
+    if constexpr (REGTW) load_pass2_twiddles<float, NC, E>(twv, t, a.tw);
     for (int i = tid; i < H; i += NT) wvad[i] = a.win_vad[i];
     for (int i = tid; i < Geo::NTW; i += NT) tw[i] = a.tw[i];
     for (int i = tid; i < N; i += NT) winh[i] = a.win_half[i];
@@ -349,7 +354,8 @@ __global__ void __launch_bounds__(DenoiseGeom<NC, F>::NT) denoise_kernel(Denoise
                     reg[m] = c2(__fmul2_rn(make_float2(s16lo(wd), s16hi(wd)), w));
                 }
             }
-            group_fft<float, NC, E, false, 0>(reg, t, buf, tw);
+            if constexpr (REGTW) group_fft_regtw<float, NC, E, false, 0>(reg, t, buf, twv);
+            else group_fft<float, NC, E, false, 0>(reg, t, buf, tw);
             group_sync<0>();
             fft_store_regs<float, NC, E>(reg, t, buf);
             __syncthreads();  // (2) spectra of all frames + VAD flags visible; this tile's PCM no longer read
@@ -426,7 +432,8 @@ __global__ void __launch_bounds__(DenoiseGeom<NC, F>::NT) denoise_kernel(Denoise
             // ---- inverse transform of frame g, time samples into the frame buffer (as floats)
             fft_load_regs<float, NC, E>(reg, t, buf);
             group_sync<0>();
-            group_fft<float, NC, E, true, 0>(reg, t, buf, tw);
+            if constexpr (REGTW) group_fft_regtw<float, NC, E, true, 0>(reg, t, buf, twv);
+            else group_fft<float, NC, E, true, 0>(reg, t, buf, tw);
             group_sync<0>();
 #pragma unroll
             for (int m = 0; m < E; ++m) buf[t + G * m] = reg[m];  // y[2n], y[2n+1] at natural positions (unpadded)
