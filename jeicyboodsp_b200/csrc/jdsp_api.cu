@@ -52,6 +52,10 @@ struct jdsp_ctx {
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
     cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};
+    // workspace of the host-buffer forms, kept across calls (cudaMalloc/cudaFree per call cost more than the copies)
+    void *ws_in[3] = {nullptr, nullptr, nullptr}, *ws_out[3] = {nullptr, nullptr, nullptr};
+    size_t ws_in_bytes = 0, ws_out_bytes = 0;
+    std::vector<struct jdsp_denoise_state *> denoise_cache;
 };
 
 static bool is_pow2(long n) { return n > 0 && (n & (n - 1)) == 0; }
@@ -135,6 +139,26 @@ static unsigned grid_for(jdsp_ctx *c, long tiles, int per_sm) {
     return (unsigned)(g < 1 ? 1 : g);
 }
 
+static int ensure_workspace(jdsp_ctx *c, size_t in_bytes, size_t out_bytes, int nslots) {
+    if (c->ws_in_bytes < in_bytes || c->ws_out_bytes < out_bytes || (nslots > 1 && !c->ws_in[1])) {
+        CU(cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < 3; ++i) {
+            if (c->pipe[i]) CU(cudaStreamSynchronize(c->pipe[i]));
+            cudaFree(c->ws_in[i]); cudaFree(c->ws_out[i]);
+            c->ws_in[i] = c->ws_out[i] = nullptr;
+        }
+        c->ws_in_bytes = in_bytes > c->ws_in_bytes ? in_bytes : c->ws_in_bytes;
+        c->ws_out_bytes = out_bytes > c->ws_out_bytes ? out_bytes : c->ws_out_bytes;
+        for (int i = 0; i < 3; ++i) {
+            CU(cudaMalloc(&c->ws_in[i], c->ws_in_bytes));
+            CU(cudaMalloc(&c->ws_out[i], c->ws_out_bytes));
+        }
+    }
+    for (int i = 0; i < 3; ++i)
+        if (!c->pipe[i]) CU(cudaStreamCreateWithFlags(&c->pipe[i], cudaStreamNonBlocking));
+    return JDSP_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------
 extern "C" {
 
@@ -179,6 +203,8 @@ int jdsp_destroy(jdsp_ctx *c) {
     cudaStreamSynchronize(c->stream);
     for (auto &kv : c->tables) cudaFree(kv.second);
     if (c->scratch) cudaFree(c->scratch);
+    for (int i = 0; i < 3; ++i) { cudaFree(c->ws_in[i]); cudaFree(c->ws_out[i]); }
+    for (auto *st : c->denoise_cache) jdsp_denoise_state_destroy(c, st);
     for (auto &p : c->pipe) if (p) cudaStreamDestroy(p);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -556,31 +582,39 @@ int jdsp_denoise_i16(jdsp_ctx *c, const jdsp_denoise_params *p, const int16_t *i
     if (n_out_samples) *n_out_samples = n_out;
     if (nb == 0) return JDSP_OK;
     CU(cudaSetDevice(c->device));
+    // per-stream state objects are cached per (params, n_streams) and reset, not re-created, on every call
     jdsp_denoise_state *st = nullptr;
-    TRY(jdsp_denoise_state_create(c, p, n_streams, &st));
+    for (auto *cand : c->denoise_cache)
+        if (cand->n_streams == n_streams && !memcmp(&cand->p, p, sizeof(*p))) st = cand;
+    if (!st) {
+        TRY(jdsp_denoise_state_create(c, p, n_streams, &st));
+        if (c->denoise_cache.size() >= 4) { jdsp_denoise_state_destroy(c, c->denoise_cache.front()); c->denoise_cache.erase(c->denoise_cache.begin()); }
+        c->denoise_cache.push_back(st);
+    } else {
+        TRY(jdsp_denoise_state_reset(c, st));
+    }
     // chunks of streams ride three CUDA streams so H2D, compute and D2H of neighbouring chunks overlap
     const long row_in = nb * H, row_out = n_out > 0 ? n_out : 8;
-    long chunk = (192L << 20) / (long)(row_in * sizeof(int16_t));
+    long chunk = (128L << 20) / (long)(row_in * sizeof(int16_t));
     if (chunk < 1) chunk = 1;
     if (chunk > n_streams) chunk = n_streams;
     const int nslots = (n_streams + chunk - 1) / chunk > 1 ? 3 : 1;
-    int16_t *d_in[3] = {nullptr, nullptr, nullptr}, *d_out[3] = {nullptr, nullptr, nullptr};
+    TRY(ensure_workspace(c, (size_t)chunk * row_in * sizeof(int16_t), (size_t)chunk * row_out * sizeof(int16_t), nslots));
+    int16_t *d_in[3], *d_out[3];
+    for (int i = 0; i < 3; ++i) { d_in[i] = (int16_t *)c->ws_in[i]; d_out[i] = (int16_t *)c->ws_out[i]; }
     int rc = JDSP_OK;
     cudaError_t e = cudaSuccess;
-    for (int i = 0; i < nslots && e == cudaSuccess; ++i) {
-        if (!c->pipe[i]) e = cudaStreamCreateWithFlags(&c->pipe[i], cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaMalloc((void **)&d_in[i], chunk * row_in * sizeof(int16_t));
-        if (e == cudaSuccess) e = cudaMalloc((void **)&d_out[i], chunk * row_out * sizeof(int16_t));
-    }
-    if (e != cudaSuccess) rc = fail(JDSP_ERR_CUDA, std::string("denoise_i16 setup: ") + cudaGetErrorString(e));
-    if (rc == JDSP_OK) {
+    {
         cudaStreamSynchronize(c->stream);  // state reset done before the pipe streams touch it
         int slot = 0;
         for (long s0 = 0; s0 < n_streams && rc == JDSP_OK; s0 += chunk, slot = (slot + 1) % nslots) {
             const long ns = n_streams - s0 < chunk ? n_streams - s0 : chunk;
             cudaStream_t q = c->pipe[slot];
-            e = cudaMemcpy2DAsync(d_in[slot], row_in * sizeof(int16_t), in + s0 * in_pitch, in_pitch * sizeof(int16_t),
-                                  n_samples * sizeof(int16_t), ns, cudaMemcpyHostToDevice, q);
+            if (in_pitch == row_in && n_samples == row_in)   // contiguous rows: one linear copy (full PCIe rate, overlaps with D2H)
+                e = cudaMemcpyAsync(d_in[slot], in + s0 * in_pitch, (size_t)ns * row_in * sizeof(int16_t), cudaMemcpyHostToDevice, q);
+            else
+                e = cudaMemcpy2DAsync(d_in[slot], row_in * sizeof(int16_t), in + s0 * in_pitch, in_pitch * sizeof(int16_t),
+                                      n_samples * sizeof(int16_t), ns, cudaMemcpyHostToDevice, q);
             if (e != cudaSuccess) { rc = fail(JDSP_ERR_CUDA, std::string("denoise_i16 H2D: ") + cudaGetErrorString(e)); break; }
             if (n_samples % H) {
                 cudaStream_t saved = c->stream; c->stream = q;
@@ -591,8 +625,11 @@ int jdsp_denoise_i16(jdsp_ctx *c, const jdsp_denoise_params *p, const int16_t *i
             rc = denoise_launch_slice(c, st, q, s0, ns, d_in[slot], row_in, nb, d_out[slot], row_out, nullptr, 0, nullptr);
             if (rc != JDSP_OK) break;
             if (n_out > 0) {
-                e = cudaMemcpy2DAsync(out + s0 * out_pitch, out_pitch * sizeof(int16_t), d_out[slot], row_out * sizeof(int16_t),
-                                      n_out * sizeof(int16_t), ns, cudaMemcpyDeviceToHost, q);
+                if (out_pitch == row_out)
+                    e = cudaMemcpyAsync(out + s0 * out_pitch, d_out[slot], (size_t)ns * row_out * sizeof(int16_t), cudaMemcpyDeviceToHost, q);
+                else
+                    e = cudaMemcpy2DAsync(out + s0 * out_pitch, out_pitch * sizeof(int16_t), d_out[slot], row_out * sizeof(int16_t),
+                                          n_out * sizeof(int16_t), ns, cudaMemcpyDeviceToHost, q);
                 if (e != cudaSuccess) { rc = fail(JDSP_ERR_CUDA, std::string("denoise_i16 D2H: ") + cudaGetErrorString(e)); break; }
             }
         }
@@ -601,8 +638,6 @@ int jdsp_denoise_i16(jdsp_ctx *c, const jdsp_denoise_params *p, const int16_t *i
             if (e != cudaSuccess && rc == JDSP_OK) rc = fail(JDSP_ERR_CUDA, std::string("denoise_i16: ") + cudaGetErrorString(e));
         }
     }
-    for (int i = 0; i < 3; ++i) { cudaFree(d_in[i]); cudaFree(d_out[i]); }
-    jdsp_denoise_state_destroy(c, st);
     return rc;
 }
 }  // extern "C"
