@@ -212,10 +212,13 @@ struct DenoiseGeom {
     static constexpr int XPAD = 32, XSLOT = H + XPAD, XBUF = (F + 1) * XSLOT;
     // shared memory carve-up (bytes, each region 16-byte aligned)
     static constexpr size_t OFF_FBUF = 0;
+    // TABLES_IN_SMEM = 0 reads window / VAD window / twiddles through the read-only global path (one copy per SM in L1
+    // instead of one per CTA): 6 KB less shared memory, 7 instead of 6 CTAs per SM -- measured 3 % SLOWER, so 1.
+    static constexpr int TABLES_IN_SMEM = 1;
     static constexpr size_t OFF_WVAD = OFF_FBUF + (size_t)F * PADN * sizeof(cf);
-    static constexpr size_t OFF_TW = OFF_WVAD + (size_t)H * sizeof(double);
-    static constexpr size_t OFF_WIN = OFF_TW + (((size_t)NTW * sizeof(cf) + 15) & ~(size_t)15);
-    static constexpr size_t OFF_CARRY = OFF_WIN + (size_t)N * sizeof(float);
+    static constexpr size_t OFF_TW = OFF_WVAD + (TABLES_IN_SMEM ? (size_t)H * sizeof(double) : 0);
+    static constexpr size_t OFF_WIN = OFF_TW + (TABLES_IN_SMEM ? (((size_t)NTW * sizeof(cf) + 15) & ~(size_t)15) : 0);
+    static constexpr size_t OFF_CARRY = OFF_WIN + (TABLES_IN_SMEM ? (size_t)N * sizeof(float) : 0);
     static constexpr size_t OFF_XS = OFF_CARRY + (size_t)2 * H * sizeof(float);
     static constexpr size_t OFF_FLAGS = OFF_XS + (size_t)2 * XBUF * sizeof(int16_t);
     static constexpr size_t OFF_BAR = OFF_FLAGS + 16 * sizeof(int);
@@ -232,9 +235,9 @@ __global__ void __launch_bounds__(DenoiseGeom<NC, F>::NT, NC == 256 ? 6 : 3) den
     constexpr int NSLOT = Geo::NSLOT, SPT = Geo::SPT, XSLOT = Geo::XSLOT, XBUF = Geo::XBUF;
     JDSP_DYN_SMEM(smem_raw);
     cf *fbuf = reinterpret_cast<cf *>(smem_raw + Geo::OFF_FBUF);
-    double *wvad = reinterpret_cast<double *>(smem_raw + Geo::OFF_WVAD);
-    cf *tw = reinterpret_cast<cf *>(smem_raw + Geo::OFF_TW);
-    float *winh = reinterpret_cast<float *>(smem_raw + Geo::OFF_WIN);
+    const double *wvad = Geo::TABLES_IN_SMEM ? reinterpret_cast<const double *>(smem_raw + Geo::OFF_WVAD) : a.win_vad;
+    const cf *tw = Geo::TABLES_IN_SMEM ? reinterpret_cast<const cf *>(smem_raw + Geo::OFF_TW) : a.tw;
+    const float *winh = Geo::TABLES_IN_SMEM ? reinterpret_cast<const float *>(smem_raw + Geo::OFF_WIN) : a.win_half;
     float *carry = reinterpret_cast<float *>(smem_raw + Geo::OFF_CARRY);
     int16_t *xsb = reinterpret_cast<int16_t *>(smem_raw + Geo::OFF_XS);
     int *flags = reinterpret_cast<int *>(smem_raw + Geo::OFF_FLAGS);
@@ -253,9 +256,14 @@ __global__ void __launch_bounds__(DenoiseGeom<NC, F>::NT, NC == 256 ? 6 : 3) den
     constexpr bool REGTW = false;
     cf twv[E - 1];
     if constexpr (REGTW) load_pass2_twiddles<float, NC, E>(twv, t, a.tw);
-    for (int i = tid; i < H; i += NT) wvad[i] = a.win_vad[i];
-    for (int i = tid; i < Geo::NTW; i += NT) tw[i] = a.tw[i];
-    for (int i = tid; i < N; i += NT) winh[i] = a.win_half[i];
+    if constexpr (Geo::TABLES_IN_SMEM) {
+        double *wv = reinterpret_cast<double *>(smem_raw + Geo::OFF_WVAD);
+        cf *twm = reinterpret_cast<cf *>(smem_raw + Geo::OFF_TW);
+        float *wh = reinterpret_cast<float *>(smem_raw + Geo::OFF_WIN);
+        for (int i = tid; i < H; i += NT) wv[i] = a.win_vad[i];
+        for (int i = tid; i < Geo::NTW; i += NT) twm[i] = a.tw[i];
+        for (int i = tid; i < N; i += NT) wh[i] = a.win_half[i];
+    }
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
     unsigned phase0 = 0, phase1 = 0;
 
