@@ -725,8 +725,10 @@ int jdsp_fastconv_state_create(jdsp_ctx *c, const jdsp_fastconv_params *p, long 
 template <int NC, int Q> static int launch_fastconv(jdsp_ctx *c, const FastconvArgs &a) {
     using Geo = FastconvGeom<NC, Q>;
     auto kfn = fastconv_kernel<NC, Q>;
-    TRY(opt_in_smem(kfn, Geo::SMEM));
-    JDSP_LAUNCH_PTR(kfn, dim3(grid_for(c, a.n_scenes, 32)), dim3(Geo::NT), Geo::SMEM, c->stream, a);
+    const size_t smem = Geo::smem(a.sources_per_scene == 1 ? 1 : 2);
+    if (smem > 227 * 1024) return fail(JDSP_ERR_UNSUPPORTED, "fast-conv scene mixing does not fit shared memory at this size");
+    TRY(opt_in_smem(kfn, smem));
+    JDSP_LAUNCH_PTR(kfn, dim3(grid_for(c, a.n_scenes, 32)), dim3(Geo::NT), smem, c->stream, a);
     return launch_check(c);
 }
 static int fastconv_run(jdsp_ctx *c, jdsp_fastconv_state *st, int sources_per_scene, const int16_t *d_in, long in_pitch, long n_blocks,

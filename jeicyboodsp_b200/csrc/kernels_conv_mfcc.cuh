@@ -36,8 +36,10 @@ struct FastconvGeom {
     // fbuf [F][PADN] cf (spectrum of the current source), ebuf [F][2][PADN] cf (per-ear accumulators / time buffers)
     static constexpr size_t OFF_FBUF = 0;
     static constexpr size_t OFF_EBUF = OFF_FBUF + (size_t)F * PADN * sizeof(cf);
-    static constexpr size_t OFF_XS = OFF_EBUF + (size_t)F * 2 * PADN * sizeof(cf);
-    static constexpr size_t SMEM = OFF_XS + 2 * (size_t)XLEN * sizeof(int16_t);
+    // one ear buffer when every scene has a single source (the second ear then overwrites the spectrum in place),
+    // two when several sources are accumulated per scene
+    __host__ __device__ static constexpr size_t off_xs(int ear_bufs) { return OFF_EBUF + (size_t)F * ear_bufs * PADN * sizeof(cf); }
+    __host__ __device__ static constexpr size_t smem(int ear_bufs) { return off_xs(ear_bufs) + 2 * (size_t)XLEN * sizeof(int16_t); }
     static_assert(B * (Q + 1) == N && B % 8 == 0, "block must divide the window into Q+1 pieces of 8k samples");
 };
 
@@ -48,9 +50,10 @@ __global__ void __launch_bounds__(FastconvGeom<NC, Q>::NT) fastconv_kernel(Fastc
     constexpr int NSLOT = Geo::NSLOT, SPT = Geo::SPT, B = Geo::B, XLEN = Geo::XLEN, BV = B / 8;
     JDSP_DYN_SMEM(smem_raw);
     cf *fbuf = reinterpret_cast<cf *>(smem_raw + Geo::OFF_FBUF);
-    cf *ebuf = reinterpret_cast<cf *>(smem_raw + Geo::OFF_EBUF);
-    int16_t *xs_base = reinterpret_cast<int16_t *>(smem_raw + Geo::OFF_XS);
     const int S = a.sources_per_scene, NE = a.n_ears;
+    cf *ebuf0 = reinterpret_cast<cf *>(smem_raw + Geo::OFF_EBUF);
+    cf *ebuf1 = (S == 1) ? fbuf : ebuf0 + F * PADN;   // ear 1: in place over the spectrum, or its own accumulator
+    int16_t *xs_base = reinterpret_cast<int16_t *>(smem_raw + Geo::off_xs(S == 1 ? 1 : 2));
     const int tid = threadIdx.x, g = tid / G, t = tid % G;
     const long n_blocks = a.n_blocks, seen0 = a.seen0, in_pitch = a.in_pitch, out_pitch = a.out_pitch, f32_pitch = a.f32_pitch;
     const long skip = seen0 < Q ? Q - seen0 : 0;  // blocks of this call that emit nothing (:118-123)
@@ -115,23 +118,32 @@ __global__ void __launch_bounds__(FastconvGeom<NC, Q>::NT) fastconv_kernel(Fastc
                     if (k < NSLOT) {
                         const int pk = pad16(k), pm = pad16((NC - k) & (NC - 1));
                         const float wc = tc[qq], wsn = ts[qq];
-                        for (int ear = 0; ear < NE; ++ear) {
-                            const cf h1 = c2(__ldg(reinterpret_cast<const float2 *>(hsrc + ear * (NC + 1) + k)));
-                            const cf h2 = c2(__ldg(reinterpret_cast<const float2 *>(hsrc + ear * (NC + 1) + NC - k)));
+                        cf h1[2], h2[2];
 #pragma unroll
-                            for (int f = 0; f < F; ++f) {
-                                const cf *fb = fbuf + f * PADN;
-                                cf X1, X2, Zk, Zm;
-                                untangle2x(fb[pk], fb[pm], wc, wsn, X1, X2);
-                                const cf Y1 = cmulw(X1, h1.x, h1.y), Y2 = cmulw(X2, h2.x, h2.y);
-                                retangle2x(Y1, Y2, wc, wsn, Zk, Zm);
-                                cf *eb = ebuf + (f * 2 + ear) * PADN;
-                                if (si == 0) {
-                                    eb[pk] = Zk; eb[pm] = Zm;
-                                } else {
-                                    const cf o1 = eb[pk];
-                                    eb[pk] = cadd(o1, Zk);
-                                    if (pm != pk) { const cf o2 = eb[pm]; eb[pm] = cadd(o2, Zm); }
+                        for (int ear = 0; ear < 2; ++ear) {
+                            const int e = ear < NE ? ear : 0;
+                            h1[ear] = c2(__ldg(reinterpret_cast<const float2 *>(hsrc + e * (NC + 1) + k)));
+                            h2[ear] = c2(__ldg(reinterpret_cast<const float2 *>(hsrc + e * (NC + 1) + NC - k)));
+                        }
+#pragma unroll
+                        for (int f = 0; f < F; ++f) {
+                            const cf *fb = fbuf + f * PADN;
+                            cf X1, X2;
+                            untangle2x(fb[pk], fb[pm], wc, wsn, X1, X2);   // read before ear 1 may overwrite these two slots
+#pragma unroll
+                            for (int ear = 0; ear < 2; ++ear) {
+                                if (ear < NE) {
+                                    cf Zk, Zm;
+                                    const cf Y1 = cmulw(X1, h1[ear].x, h1[ear].y), Y2 = cmulw(X2, h2[ear].x, h2[ear].y);
+                                    retangle2x(Y1, Y2, wc, wsn, Zk, Zm);
+                                    cf *eb = (ear == 0 ? ebuf0 : ebuf1) + f * PADN;
+                                    if (si == 0) {
+                                        eb[pk] = Zk; eb[pm] = Zm;
+                                    } else {
+                                        const cf o1 = eb[pk];
+                                        eb[pk] = cadd(o1, Zk);
+                                        if (pm != pk) { const cf o2 = eb[pm]; eb[pm] = cadd(o2, Zm); }
+                                    }
                                 }
                             }
                         }
@@ -148,7 +160,7 @@ __global__ void __launch_bounds__(FastconvGeom<NC, Q>::NT) fastconv_kernel(Fastc
             // ---- inverse transforms, keep samples [n_taps-1, n_taps-1+B) = the last B of the window (:156-158)
             for (int ear = 0; ear < NE; ++ear) {
                 cf reg[E];
-                cf *buf = ebuf + (g * 2 + ear) * PADN;
+                cf *buf = (ear == 0 ? ebuf0 : ebuf1) + g * PADN;
                 fft_load_regs<float, NC, E>(reg, t, buf);
                 group_sync<SYNC>();
                 group_fft<float, NC, E, true, SYNC>(reg, t, buf, tw);
@@ -165,7 +177,7 @@ __global__ void __launch_bounds__(FastconvGeom<NC, Q>::NT) fastconv_kernel(Fastc
                     const int f = it / (B / 4), n = (it % (B / 4)) * 4;
                     const long blk = b0 + f - skip;
                     if (f < nf && blk >= 0) {
-                        const float4 y = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(ebuf + (f * 2 + ear) * PADN) + (N - B) + n);
+                        const float4 y = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>((ear == 0 ? ebuf0 : ebuf1) + f * PADN) + (N - B) + n);
                         const uint32_t lo = ((uint32_t)(uint16_t)trunc16(y.x)) | ((uint32_t)(uint16_t)trunc16(y.y) << 16);
                         const uint32_t hi = ((uint32_t)(uint16_t)trunc16(y.z)) | ((uint32_t)(uint16_t)trunc16(y.w) << 16);
                         *reinterpret_cast<uint2 *>(orow + blk * B + n) = make_uint2(lo, hi);
