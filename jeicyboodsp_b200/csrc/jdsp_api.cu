@@ -855,7 +855,7 @@ int jdsp_mfcc_plan_create(jdsp_ctx *c, const jdsp_mfcc_params *p, jdsp_mfcc_plan
     if (p->n_fft != 512 && p->n_fft != 1024) return fail(JDSP_ERR_UNSUPPORTED, "MFCC supports n_fft 512 or 1024");
     REQUIRE(p->frame_len >= 8 && p->frame_len <= p->n_fft && p->frame_len % 8 == 0, "frame_len must be a multiple of 8 and <= n_fft");
     REQUIRE(p->hop >= 8 && p->hop % 8 == 0, "hop must be a multiple of 8 samples (16-byte bulk copies)");
-    REQUIRE(p->n_mel >= 1 && p->n_mel <= 64 && p->n_cep >= 1 && p->n_cep <= 32, "n_mel <= 64 and n_cep <= 32");
+    REQUIRE(p->n_mel >= 1 && p->n_mel <= 64 && p->n_cep >= 1 && p->n_cep <= 16, "n_mel <= 64 and n_cep <= 16");
     CU(cudaSetDevice(c->device));
     jdsp_mfcc_plan *pl = new jdsp_mfcc_plan();
     pl->p = *p;

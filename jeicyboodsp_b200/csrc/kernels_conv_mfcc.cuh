@@ -211,13 +211,13 @@ struct MfccGeom {
     static constexpr int NSLOT = NC / 2 + 1;
     static constexpr int SPT = (NSLOT + NT - 1) / NT;
     static constexpr int MAXMEL = 64, MAXCEP = 32;
-    static constexpr int MAGP = F + 1;               // |X| is stored [bin][frame] with an odd pitch: conflict-free both ways
+    static constexpr int FP = PADN + 1;              // frame pitch in complex slots: odd in 8-byte units mod 16, so the
+                                                     // cross-frame reads of the mel stage hit different banks
     static constexpr size_t OFF_FBUF = 0;
-    static constexpr size_t OFF_MAG = OFF_FBUF + (size_t)F * PADN * sizeof(cf);
-    static constexpr size_t OFF_MEL = OFF_MAG + (((size_t)NC * MAGP * sizeof(float)) + 15 & ~(size_t)15);
-    static constexpr size_t OFF_MELW = OFF_MEL + (size_t)F * MAXMEL * sizeof(float);       // [NC] filterbank weights
-    static constexpr size_t OFF_DCT = OFF_MELW + (size_t)NC * sizeof(float);              // [MAXMEL][MAXCEP] (cepstrum index fastest)
-    static constexpr size_t OFF_START = OFF_DCT + (size_t)MAXCEP * MAXMEL * sizeof(float); // [MAXMEL+2]
+    static constexpr size_t OFF_MEL = OFF_FBUF + ((((size_t)F * FP * sizeof(cf)) + 15) & ~(size_t)15);
+    static constexpr size_t OFF_MELW = OFF_MEL + (size_t)F * MAXMEL * sizeof(float);       // [2][NC]: 1-w, w
+    static constexpr size_t OFF_DCT = OFF_MELW + (size_t)2 * NC * sizeof(float);          // [n_mel][16] (cepstrum index fastest)
+    static constexpr size_t OFF_START = OFF_DCT + (size_t)MAXMEL * 16 * sizeof(float);     // [MAXMEL+2]
     static constexpr size_t OFF_WINH = OFF_START + (size_t)(MAXMEL + 8) * sizeof(int);     // [N] half window (zero past frame_len)
     static constexpr size_t OFF_BAR = OFF_WINH + (size_t)N * sizeof(float);
     static constexpr size_t OFF_XS = OFF_BAR + 16;
@@ -232,10 +232,9 @@ template <int NC>
 __global__ void __launch_bounds__(MfccGeom<NC>::NT) mfcc_kernel(MfccArgs a) {
     using Geo = MfccGeom<NC>;
     constexpr int E = Geo::E, G = Geo::G, NT = Geo::NT, F = Geo::F, PADN = Geo::PADN, NSLOT = Geo::NSLOT, SPT = Geo::SPT;
-    constexpr int MAGP = Geo::MAGP, MAXMEL = Geo::MAXMEL, MAXCEP = Geo::MAXCEP;
+    constexpr int FP = Geo::FP, MAXMEL = Geo::MAXMEL, DP = 16;
     JDSP_DYN_SMEM(smem_raw);
     cf *fbuf = reinterpret_cast<cf *>(smem_raw + Geo::OFF_FBUF);
-    float *mag = reinterpret_cast<float *>(smem_raw + Geo::OFF_MAG);
     float *mel = reinterpret_cast<float *>(smem_raw + Geo::OFF_MEL);
     float *melw = reinterpret_cast<float *>(smem_raw + Geo::OFF_MELW);
     float *dct = reinterpret_cast<float *>(smem_raw + Geo::OFF_DCT);
@@ -249,8 +248,8 @@ __global__ void __launch_bounds__(MfccGeom<NC>::NT) mfcc_kernel(MfccArgs a) {
     const cf *tw = a.tw;
     const size_t span_b = Geo::span_bytes(W, hop);
     int16_t *xsb = reinterpret_cast<int16_t *>(smem_raw + Geo::OFF_XS);
-    for (int i = tid; i < NC; i += NT) melw[i] = a.mel_w[i];
-    for (int i = tid; i < NCEP * C; i += NT) dct[(i % C) * MAXCEP + (i / C)] = a.dct[i];
+    for (int i = tid; i < NC; i += NT) { const float w = a.mel_w[i]; melw[i] = 1.f - w; melw[NC + i] = w; }
+    for (int i = tid; i < NCEP * C; i += NT) dct[(i % C) * DP + (i / C)] = a.dct[i];
     for (int i = tid; i < C + 2; i += NT) mstart[i] = a.mel_start[i];
     for (int i = tid; i < 2 * NC; i += NT) winh[i] = i < W ? a.win_half[i] : 0.f;
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
@@ -286,7 +285,7 @@ __global__ void __launch_bounds__(MfccGeom<NC>::NT) mfcc_kernel(MfccArgs a) {
         if (tid == 0 && tile + gridDim.x < n_tiles) issue(tile + gridDim.x, cur ^ 1);
         // ---- pre-emphasis (:208-210), window (:212-214), packed real transform of frame g ------------
         cf reg[E];
-        cf *buf = fbuf + g * PADN;
+        cf *buf = fbuf + g * FP;
         {
             const uint32_t *fw = reinterpret_cast<const uint32_t *>(xs + g * hop) + t;
             const float2 *w2 = reinterpret_cast<const float2 *>(winh) + t;
@@ -309,35 +308,34 @@ __global__ void __launch_bounds__(MfccGeom<NC>::NT) mfcc_kernel(MfccArgs a) {
         group_sync<0>();
         fft_store_regs<float, NC, E>(reg, t, buf);
         __syncthreads();  // (C)
-        // ---- |X[i]|, i < n_fft/2 (:218-220), stored [bin][frame] ------------------------------------------
+        // ---- |X[i]|, i < n_fft/2 (:218-220), written in place over the real lane of the spectrum slots this thread owns
 #pragma unroll
         for (int qq = 0; qq < SPT; ++qq) {
             const int k = tid + qq * NT;
             if (k < NSLOT) {
                 const int pk = pad16(k), pm = pad16((NC - k) & (NC - 1));
                 const float wc = tc[qq], wsn = ts[qq];
-                const bool second = (k > 0 && k < NC - k);
 #pragma unroll
                 for (int f = 0; f < F; ++f) {
-                    const cf *fb = fbuf + f * PADN;
+                    cf *fb = fbuf + f * FP;
                     cf X1, X2;
                     untangle2x(fb[pk], fb[pm], wc, wsn, X1, X2);
-                    if (k < NC) mag[k * MAGP + f] = sqrt_fast(X1.x * X1.x + X1.y * X1.y);
-                    if (second) mag[(NC - k) * MAGP + f] = sqrt_fast(X2.x * X2.x + X2.y * X2.y);
+                    if (k > 0 && k < NC - k) fb[pm].x = sqrt_fast(X2.x * X2.x + X2.y * X2.y);   // bin NC-k
+                    fb[pk].x = sqrt_fast(X1.x * X1.x + X1.y * X1.y);                             // bin k (bin NC itself is unused)
                 }
             }
         }
         __syncthreads();  // (D)
         // ---- M3 MelFilterBank (:154-174): channel c collects (1-w)*a over bins with index c and w*a over index c+1.
         // Item = (channel, frame) with the frame fastest, so the lanes of a warp walk 4 neighbouring channels of
-        // similar width and read consecutive floats.
+        // similar width.
         for (int it = tid; it < C * F; it += NT) {
             const int c = it / F, f = it % F;
             const int i0 = mstart[c], i1 = mstart[c + 1], i2 = mstart[c + 2];
-            const float *mg = mag + f;
+            const cf *mg = fbuf + f * FP;
             float acc = 0.f;
-            for (int i = i0; i < i1; ++i) acc = fmaf(1.f - melw[i], mg[i * MAGP], acc);
-            for (int i = i1; i < i2; ++i) acc = fmaf(melw[i], mg[i * MAGP], acc);
+            for (int i = i0; i < i1; ++i) acc = fmaf(melw[i], mg[pad16(i)].x, acc);
+            for (int i = i1; i < i2; ++i) acc = fmaf(melw[NC + i], mg[pad16(i)].x, acc);
             mel[f * MAXMEL + c] = logf(acc);  // :170-172
         }
         __syncthreads();  // (E)
@@ -346,7 +344,7 @@ __global__ void __launch_bounds__(MfccGeom<NC>::NT) mfcc_kernel(MfccArgs a) {
             const int f = it / NCEP, i = it % NCEP;
             const float *ml = mel + f * MAXMEL;
             float acc = 0.f;
-            for (int c = 0; c < C; ++c) acc = fmaf(dct[c * MAXCEP + i], ml[c], acc);
+            for (int c = 0; c < C; ++c) acc = fmaf(dct[c * DP + i], ml[c], acc);
             a.feat[u * feat_pitch + (t0 + f) * NCEP + i] = acc;
         }
         cur ^= 1;
