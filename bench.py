@@ -240,6 +240,9 @@ def main_gpu(args):
                 for m in (SS, WIENER)}
     avg_kernel_ms = statistics.mean(kern_ms)
     achieved = alg_bytes / (avg_kernel_ms * 1e-3) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this exact workload, from the committed
+    # `ncu --set full` capture profiles/round1/ncu_bench_kernel_summary.txt (7.882 GB read + 7.837 GB written)
+    traffic = 15_718_634_000 if (S == 4096 and n == 960_000) else None
 
     # ---- parity spot check on the very data that was timed (8 streams through the oracle) -------------------
     parity = None
@@ -314,7 +317,7 @@ def main_gpu(args):
                        "l2": f"inputs {S * n * 2 / 1e9:.2f} GB per pass >> 126 MB L2 (no flush needed)",
                        "frames_per_s": value * 1e6 / HOP},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                         "traffic": None, "peak_source": peak_src, "kernel": "jdsp::denoise_kernel<256,8,MODE>",
+                         "traffic": traffic, "traffic_source": "ncu --set full capture of this launch, profiles/round1/ncu_bench_kernel_summary.txt", "peak_source": peak_src, "kernel": "jdsp::denoise_kernel<256,8,MODE>",
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_kernel_ms, "per_mode_ms": per_mode,
                          "note": "4 B/sample (int16 in + int16 out); the kernel is fp32-issue/shared-memory bound, see DESIGN.md"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "parity": parity,
