@@ -3,8 +3,8 @@
 // Replaces FFTProcess + Bitrev (FFTAlgorithm_ver2.cpp:94-149,186-207) for arbitrary batches.
 // Unnormalised in both directions like the reference (:75-80 divides by N in the caller).
 //   N <= 8192 : one thread group per transform, whole transform on chip, one HBM read + one write.
-//   N >= 16384: four-step (N = N1*N2) as two kernels over a small reusable scratch buffer that
-//               stays resident in the 126 MB L2, so HBM still sees ~one read + one write.
+//   N >= 16384: four-step (N = N1*N2) as two kernels over a scratch buffer (two HBM round trips; an
+//               L2-resident chunking was measured slower because the per-launch ramp dominates).
 #pragma once
 #include "jdsp_device.cuh"
 
