@@ -1,0 +1,95 @@
+"""Error behaviour and boundary conditions of the C ABI (both backends): invalid arguments return JDSP_ERR_INVALID /
+JDSP_ERR_UNSUPPORTED with a message instead of computing garbage; padded row pitches, state reset and multiple
+contexts behave."""
+import numpy as np
+import pytest
+
+from jeicyboodsp_b200 import synth
+from jeicyboodsp_b200.binding import SS, Context, JdspError
+
+_CACHE = {}
+
+
+@pytest.fixture(params=["emul", pytest.param("gpu", marks=pytest.mark.gpu)])
+def be(request):
+    if request.param not in _CACHE:
+        from backends import EmulBackend, GpuBackend
+        _CACHE[request.param] = EmulBackend() if request.param == "emul" else GpuBackend()
+    return _CACHE[request.param]
+
+
+def test_invalid_arguments_are_rejected(be):
+    z = be.zeros((1, 48), np.complex64)
+    with pytest.raises(JdspError) as e:
+        be.ctx.fft_c2c_f32(z, z, 48, 1, True)                 # not a power of two
+    assert e.value.code == -1
+    with pytest.raises(JdspError) as e:
+        be.ctx.fft_c2c_f32(be.zeros((1, 1 << 17), np.complex64), be.zeros((1, 1 << 17), np.complex64), 1 << 17, 1, True)
+    assert e.value.code == -4                                  # JDSP_ERR_UNSUPPORTED above 2^16
+    p = be.L.denoise_params("bench", SS)
+    p.n_fft = 2048                                             # n_fft != 2*hop
+    with pytest.raises(JdspError):
+        be.ctx.denoise_state(p, 1)
+    p = be.L.denoise_params("bench", SS)
+    st = be.ctx.denoise_state(p, 2)
+    x = be.zeros((2, 10 * p.hop + 4), np.int16)
+    out = be.zeros((2, 8 * p.hop + 4), np.int16)
+    with pytest.raises(JdspError) as e:                        # row pitch not a multiple of 8 samples
+        st.run(x, 10 * p.hop + 4, 10, out, 8 * p.hop + 4)
+    assert "16-byte" in str(e.value)
+    st.close()
+    with pytest.raises(JdspError):
+        be.L.denoise_params("nope", SS)
+    with pytest.raises(JdspError):
+        be.L.mfcc_params("nope")
+    m = be.L.mfcc_params("bench")
+    m.hop = 100                                                # not a multiple of 8 samples
+    with pytest.raises(JdspError):
+        be.ctx.mfcc_plan(m)
+    f = be.L.fastconv_params("bench")
+    f.n_taps = 400                                             # must be history*block + 1
+    with pytest.raises(JdspError):
+        be.ctx.fastconv_state(f, 1, np.zeros((1, 2, 400)))
+
+
+def test_padded_pitches_and_state_reset(be, oracle):
+    from oracle.oracle import DenoiseParams as ODP
+    p = be.L.denoise_params("bench", SS)
+    H, nb, S = p.hop, 40, 2
+    x = np.stack([synth.denoise_stream(60 + s, nb * H) for s in range(S)])
+    pitch_in, pitch_out = nb * H + 64, (nb - 2) * H + 24      # rows padded beyond the payload
+    xin = np.full((S, pitch_in), 12345, np.int16)
+    xin[:, : nb * H] = x
+    d_in, d_out = be.to_dev(xin), be.zeros((S, pitch_out), np.int16)
+    st = be.ctx.denoise_state(p, S)
+    for _ in range(2):                                         # second pass after reset must reproduce the first
+        st.reset()
+        assert st.run(d_in, pitch_in, nb, d_out, pitch_out) == nb - 2
+        out = be.to_host(d_out)
+        for s in range(S):
+            ref = oracle.denoise(x[s], ODP.preset("bench", SS)).out
+            assert np.abs(out[s, : (nb - 2) * H].astype(int) - ref.astype(int)).max() <= 1
+            assert np.all(out[s, (nb - 2) * H:] == 0)          # padding untouched
+    st.close()
+
+
+def test_two_contexts_are_independent(be):
+    ctx2 = Context(be.L, 0)
+    rng = np.random.default_rng(3)
+    z = rng.normal(size=(2, 512)) + 1j * rng.normal(size=(2, 512))
+    a = be.ctx.fft_process(z, True)
+    b = ctx2.fft_process(z, True)
+    assert np.array_equal(a, b)
+    assert ctx2.kernel_launches() >= 1
+    ctx2.close()
+
+
+def test_empty_batches_are_no_ops(be):
+    z = be.zeros((1, 64), np.complex64)
+    be.ctx.fft_c2c_f32(z, z, 64, 0, True)
+    p = be.L.mfcc_params("bench")
+    plan = be.ctx.mfcc_plan(p)
+    assert plan.n_frames(399) == 0
+    feat = be.zeros((1, 1, 13), np.float32)
+    assert plan.run(be.zeros((1, 392), np.int16), 392, 1, 392, feat, 13) == 0
+    plan.close()
