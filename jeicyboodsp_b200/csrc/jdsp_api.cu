@@ -277,6 +277,43 @@ static int launch_c2c_fourstep(jdsp_ctx *c, const cx<T> *in, cx<T> *out, long ba
     }
     return JDSP_OK;
 }
+// fp32 N >= 16384, opt-in (JDSP_FFT_FUSED=1): one persistent kernel, column and row passes pipelined through an L2-resident
+// scratch ring.  Measured equal to the two-kernel plan (2.36-2.48 vs 2.33-2.41 TB/s; barrier-stall bound, scratch still spills
+// ~0.8 B per algorithmic byte to HBM), so the two-kernel plan stays the default.
+template <int N1, int N2, bool INV>
+static int launch_c2c_fused(jdsp_ctx *c, const cx<float> *in, cx<float> *out, long batch) {
+    using Geo = FusedGeom<float, N1, N2, INV>;
+    const long N = (long)N1 * N2;
+    void *tw1, *tw2, *twN;
+    TRY(get_table(c, 0, N1, &tw1));
+    TRY(get_table(c, 0, N2, &tw2));
+    TRY(get_table(c, 3, (int)N, &twN));
+    auto kfn = fft_fourstep_fused_kernel<float, N1, N2, INV>;
+    TRY(opt_in_smem(kfn, Geo::SMEM));
+    int per_sm = 1;
+#ifndef JDSP_EMUL
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, Geo::THREADS, Geo::SMEM));
+    if (per_sm < 1) return fail(JDSP_ERR_CUDA, "fused FFT kernel does not fit an SM");
+    const long grid_cap = (long)per_sm * c->sm_count;   // every CTA must be resident: items wait on one another
+#else
+    const long grid_cap = 1;                            // the emulator runs CTAs one after another
+#endif
+    // look-ahead: enough transforms in flight that a row item is rarely grabbed before its columns are done
+    long look = (2 * grid_cap + Geo::TA + Geo::TB - 1) / (Geo::TA + Geo::TB) + 2;
+    if (look > batch) look = batch;
+    const long ring = 2 * look;
+    TRY(ensure_scratch(c, (size_t)ring * N * sizeof(cx<float>) + (2 * (size_t)batch + 8) * sizeof(unsigned)));
+    cx<float> *tmp = (cx<float> *)c->scratch;
+    unsigned *ctr = (unsigned *)((char *)c->scratch + (size_t)ring * N * sizeof(cx<float>));
+    CU(cudaMemsetAsync(ctr, 0, (2 * (size_t)batch + 8) * sizeof(unsigned), c->stream));
+    FusedFftSync sy{ctr, ctr + 8, ctr + 8 + batch};
+    const long n_items = batch * (Geo::TA + Geo::TB);
+    const long grid = n_items < grid_cap ? n_items : grid_cap;
+    JDSP_LAUNCH_PTR(kfn, dim3((unsigned)grid), dim3(Geo::THREADS), Geo::SMEM, c->stream, in, tmp, out, batch, (int)look, (int)ring,
+                    (const cx<float> *)tw1, (const cx<float> *)tw2, (const cx<float> *)twN, 1.0f, sy);
+    return launch_check(c);
+}
+
 template <typename T, bool INV>
 static int fft_dispatch(jdsp_ctx *c, const cx<T> *in, cx<T> *out, int n, long batch) {
     const int tkind = sizeof(T) == 4 ? 0 : 1;
@@ -287,9 +324,15 @@ static int fft_dispatch(jdsp_ctx *c, const cx<T> *in, cx<T> *out, int n, long ba
 #define SMALL(NN) case NN: return launch_c2c_small<T, NN, INV>(c, in, out, batch, t);
         SMALL(2) SMALL(4) SMALL(8) SMALL(16) SMALL(32) SMALL(64) SMALL(128) SMALL(256) SMALL(512) SMALL(1024) SMALL(2048) SMALL(4096) SMALL(8192)
 #undef SMALL
-        case 16384: return launch_c2c_fourstep<T, 64, 256, INV>(c, in, out, batch, tkind);
-        case 32768: return launch_c2c_fourstep<T, 128, 256, INV>(c, in, out, batch, tkind);
-        case 65536: return launch_c2c_fourstep<T, 256, 256, INV>(c, in, out, batch, tkind);
+        case 16384:
+            if constexpr (sizeof(T) == 4) { if (getenv("JDSP_FFT_FUSED")) return launch_c2c_fused<64, 256, INV>(c, in, out, batch); }
+            return launch_c2c_fourstep<T, 64, 256, INV>(c, in, out, batch, tkind);
+        case 32768:
+            if constexpr (sizeof(T) == 4) { if (getenv("JDSP_FFT_FUSED")) return launch_c2c_fused<128, 256, INV>(c, in, out, batch); }
+            return launch_c2c_fourstep<T, 128, 256, INV>(c, in, out, batch, tkind);
+        case 65536:
+            if constexpr (sizeof(T) == 4) { if (getenv("JDSP_FFT_FUSED")) return launch_c2c_fused<256, 256, INV>(c, in, out, batch); }
+            return launch_c2c_fourstep<T, 256, 256, INV>(c, in, out, batch, tkind);
         default: return fail(JDSP_ERR_UNSUPPORTED, "FFT length must be a power of two in [2, 65536]");
     }
 }

@@ -202,4 +202,153 @@ fft_rows_kernel(const cx<T> *__restrict__ tmp, cx<T> *__restrict__ out, int N1, 
     }
 }
 
+// ---- fused four-step: ONE persistent kernel, intermediate kept in L2 -------------------------------------------
+// Work items are pulled from a global counter in an order that interleaves the column pass of transform s with the row
+// pass of transform s - LOOK.  A row item waits (rarely) until all column tiles of its transform have been published;
+// a column item waits until the scratch slot it is about to overwrite has been fully consumed.  Every CTA of the grid
+// is resident (the host sizes the grid from the occupancy query), items are handed out in dependency order, so the
+// waits always terminate.  The scratch ring (2*LOOK transforms) stays in the 126 MB L2: HBM sees one read + one write.
+struct FusedFftSync {
+    unsigned *queue;     // next work item
+    unsigned *done_a;    // [batch] column tiles finished per transform
+    unsigned *done_b;    // [batch] row tiles finished per transform
+};
+JDSP_DEV unsigned ld_acquire_u32(const unsigned *p) {
+#ifdef JDSP_EMUL
+    return *p;
+#else
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+#endif
+}
+template <typename T> JDSP_DEV cx<T> ld_cg(const cx<T> *p) {   // scratch written by other SMs: bypass this SM's L1
+#ifdef JDSP_EMUL
+    return *p;
+#else
+    if constexpr (sizeof(T) == 4) { const float2 v = __ldcg(reinterpret_cast<const float2 *>(p)); return cmake<T>(v.x, v.y); }
+    else { const double2 v = __ldcg(reinterpret_cast<const double2 *>(p)); return cmake<T>(v.x, v.y); }
+#endif
+}
+template <typename T, int N1, int N2, bool INV>
+struct FusedGeom {
+    static constexpr int THREADS = 512;
+    static constexpr int G1 = FftGeom<N1>::G, G2 = FftGeom<N2>::G, E = 16;
+    static constexpr int CT = THREADS / G1, RT = THREADS / G2;      // columns per column tile, rows per row tile
+    static constexpr int TA = N2 / CT, TB = N1 / RT;                // tiles per transform
+    static constexpr int P1 = FftGeom<N1>::PADN + 1, P2 = FftGeom<N2>::PADN + 1;
+    static constexpr size_t SMEM_A = (size_t)CT * P1 * sizeof(cx<T>), SMEM_B = (size_t)RT * P2 * sizeof(cx<T>);
+    static constexpr size_t SMEM = (SMEM_A > SMEM_B ? SMEM_A : SMEM_B) + 16;
+    static_assert(N1 / G1 == E && N2 / G2 == E && G1 <= 32 && G2 >= 16 && G2 <= 32, "16 points per thread, warp-level groups");
+    static_assert(TA >= 1 && TB >= 1 && N2 % CT == 0 && N1 % RT == 0, "tiles must divide the transform");
+};
+template <typename T, int N1, int N2, bool INV>
+__global__ void __launch_bounds__(512, 2)
+fft_fourstep_fused_kernel(const cx<T> *__restrict__ in, cx<T> *tmp, cx<T> *__restrict__ out, long batch, int look, int ring,
+                          const cx<T> *__restrict__ tw1, const cx<T> *__restrict__ tw2, const cx<T> *__restrict__ twN, T scale,
+                          FusedFftSync sy) {
+    using Geo = FusedGeom<T, N1, N2, INV>;
+    constexpr int E = Geo::E, G1 = Geo::G1, G2 = Geo::G2, CT = Geo::CT, RT = Geo::RT, TA = Geo::TA, TB = Geo::TB;
+    constexpr int P1 = Geo::P1, P2 = Geo::P2, THREADS = Geo::THREADS;
+    constexpr long N = (long)N1 * N2;
+    JDSP_DYN_SMEM(smem_raw);
+    cx<T> *sm = reinterpret_cast<cx<T> *>(smem_raw + 16);
+    unsigned *item_sh = reinterpret_cast<unsigned *>(smem_raw);
+    // item numbering: steps 0..look-1 hold TA column items; steps look..batch-1 hold TA column + TB row items;
+    // steps batch..batch+look-1 hold TB row items (rows of transform step-look)
+    const long lk = look < batch ? look : batch;
+    const long n_head = lk * TA, n_mid = (batch - lk) * (TA + TB), n_items = n_head + n_mid + lk * TB;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) *item_sh = atomicAdd(sy.queue, 1u);
+        __syncthreads();
+        const long g = *item_sh;
+        if (g >= n_items) break;
+        long f; int tile; bool is_rows;
+        if (g < n_head) { f = g / TA; tile = (int)(g % TA); is_rows = false; }
+        else if (g < n_head + n_mid) {
+            const long r = g - n_head, step = lk + r / (TA + TB); const int j = (int)(r % (TA + TB));
+            if (j < TA) { f = step; tile = j; is_rows = false; } else { f = step - lk; tile = j - TA; is_rows = true; }
+        } else { const long r = g - n_head - n_mid; f = (batch - lk) + r / TB; tile = (int)(r % TB); is_rows = true; }
+        cx<T> *slot = tmp + (f % ring) * N;
+        if (!is_rows) {
+            // ---- column tile: DFT over n1 for CT adjacent columns, twiddle, write [k1][n2] into the scratch slot
+            if (f >= ring) {   // the slot's previous tenant must have been read completely
+                if (threadIdx.x == 0) while (ld_acquire_u32(sy.done_b + (f - ring)) < (unsigned)TB) { }
+                __syncthreads();
+            }
+            const int c0 = tile * CT;
+            const int sc = threadIdx.x % CT, sr = threadIdx.x / CT;
+            const int c = threadIdx.x / G1, t = threadIdx.x % G1;
+            const cx<T> *src = in + f * N + c0 + sc;
+            cx<T> st[E];
+#pragma unroll
+            for (int i = 0; i < E; ++i) st[i] = src[(long)(sr + (THREADS / CT) * i) * N2];
+            const long col = c0 + c;
+            const cx<T> wa = twN[col * t], b1 = twN[col * G1], b4 = twN[col * (4 * G1)];
+#pragma unroll
+            for (int i = 0; i < E; ++i) sm[sc * P1 + pad16(sr + (THREADS / CT) * i)] = st[i];
+            __syncthreads();
+            cx<T> reg[E];
+            cx<T> *buf = sm + c * P1;
+            fft_load_regs<T, N1, E>(reg, t, buf);
+            group_sync<0>();
+            group_fft<T, N1, E, INV, 0>(reg, t, buf, tw1);
+            group_sync<0>();
+            {
+                const cx<T> b2 = cmul<false>(b1, b1), b3 = cmul<false>(b2, b1);
+                const cx<T> b8 = cmul<false>(b4, b4), b12 = cmul<false>(b8, b4);
+                cx<T> aj[4];
+                aj[0] = wa; aj[1] = cmul<false>(wa, b4); aj[2] = cmul<false>(wa, b8); aj[3] = cmul<false>(wa, b12);
+#pragma unroll
+                for (int m = 0; m < E; ++m) {
+                    const int r = m & 3;
+                    cx<T> w = aj[m >> 2];
+                    if (r == 1) w = cmul<false>(w, b1);
+                    if (r == 2) w = cmul<false>(w, b2);
+                    if (r == 3) w = cmul<false>(w, b3);
+                    reg[m] = cmul<INV>(reg[m], w);
+                }
+            }
+            fft_store_regs<T, N1, E>(reg, t, buf);
+            __syncthreads();
+            cx<T> *dst = slot + c0 + sc;
+#pragma unroll
+            for (int i = 0; i < E; ++i) {
+                const int k1 = sr + (THREADS / CT) * i;
+                dst[(long)k1 * N2] = sm[sc * P1 + pad16(k1)];
+            }
+            __threadfence();          // publish the tile before the counter moves
+            __syncthreads();
+            if (threadIdx.x == 0) atomicAdd(sy.done_a + f, 1u);
+        } else {
+            // ---- row tile: RT adjacent rows k1 of the scratch slot, DFT over n2, write X[k1 + N1*k2]
+            if (threadIdx.x == 0) while (ld_acquire_u32(sy.done_a + f) < (unsigned)TA) { }
+            __syncthreads();
+            const int r0 = tile * RT;
+            const int r = threadIdx.x / G2, t = threadIdx.x % G2;
+            const int orr = threadIdx.x % RT, ok = threadIdx.x / RT;
+            const cx<T> *src = slot + (long)(r0 + r) * N2 + t;
+            cx<T> reg[E];
+#pragma unroll
+            for (int m = 0; m < E; ++m) reg[m] = ld_cg(src + G2 * m);
+            cx<T> *buf = sm + r * P2;
+            group_fft<T, N2, E, INV, 0>(reg, t, buf, tw2);
+            group_sync<0>();
+            fft_store_regs<T, N2, E>(reg, t, buf);
+            __syncthreads();
+            cx<T> *dst = out + f * N + r0 + orr;
+#pragma unroll
+            for (int i = 0; i < E; ++i) {
+                const int k2 = ok + (THREADS / RT) * i;
+                cx<T> v = sm[orr * P2 + pad16(k2)];
+                v.x *= scale; v.y *= scale;
+                dst[(long)k2 * N1] = v;
+            }
+            __syncthreads();          // all reads of the scratch slot by this tile are complete
+            if (threadIdx.x == 0) { __threadfence(); atomicAdd(sy.done_b + f, 1u); }
+        }
+    }
+}
+
 }  // namespace jdsp
