@@ -1,0 +1,339 @@
+// jdsp_conv_mfcc.cu -- C ABI (include/jdsp.h), part 3: the fast-convolution and MFCC pipelines.
+#include "jdsp_host.hpp"
+#include "kernels_conv_mfcc.cuh"
+
+// ---------------------------------------------------------------------------------------------------
+// Fast convolution
+struct jdsp_fastconv_state {
+    jdsp_fastconv_params p;
+    long n_sources = 0;
+    long seen = 0;
+    cf *d_hs = nullptr;          // [n_filters][ears][NC+1] pre-scaled by 1/(2*n_fft)
+    int16_t *d_hist = nullptr;   // [source][q*B]
+};
+
+extern "C" {
+int jdsp_fastconv_params_preset(const char *name, jdsp_fastconv_params *p) {
+    REQUIRE(name && p, "null argument");
+    memset(p, 0, sizeof(*p));
+    if (!strcmp(name, "ref")) {          // Fast_Convolution_Based_3DAudio_Impl.cpp:47-49, FilterCoefficient.h:1-2
+        p->block = 1024; p->n_fft = 8192; p->history_blocks = 7; p->n_taps = 7169; p->n_ears = 1; p->shared_filter = 1;
+    } else if (!strcmp(name, "bench")) { // BASELINE.json config 3
+        p->block = 512; p->n_fft = 1024; p->history_blocks = 1; p->n_taps = 513; p->n_ears = 2; p->shared_filter = 0;
+    } else {
+        return fail(JDSP_ERR_INVALID, "unknown fast-conv preset (ref | bench)");
+    }
+    return JDSP_OK;
+}
+int jdsp_fastconv_state_reset(jdsp_ctx *c, jdsp_fastconv_state *st) {
+    REQUIRE(c && st, "null argument");
+    CU(cudaMemsetAsync(st->d_hist, 0, (size_t)st->n_sources * st->p.history_blocks * st->p.block * sizeof(int16_t), c->stream));
+    st->seen = 0;
+    return JDSP_OK;
+}
+int jdsp_fastconv_state_destroy(jdsp_ctx *c, jdsp_fastconv_state *st) {
+    if (!st) return JDSP_OK;
+    REQUIRE(c, "ctx is null");
+    cudaStreamSynchronize(c->stream);
+    cudaFree(st->d_hs);
+    cudaFree(st->d_hist);
+    delete st;
+    return JDSP_OK;
+}
+int jdsp_fastconv_state_create(jdsp_ctx *c, const jdsp_fastconv_params *p, long n_sources, const double *taps, jdsp_fastconv_state **out) {
+    REQUIRE(c && p && taps && out, "null argument");
+    REQUIRE(n_sources >= 1, "n_sources must be >= 1");
+    REQUIRE(p->n_ears == 1 || p->n_ears == 2, "n_ears must be 1 or 2");
+    REQUIRE(p->n_fft == (p->history_blocks + 1) * p->block, "n_fft must equal (history_blocks+1)*block");
+    REQUIRE(p->n_taps >= 1 && p->n_taps == p->history_blocks * p->block + 1, "n_taps must equal history_blocks*block + 1 (the reference keeps y[n_taps-1 ..])");
+    REQUIRE(p->block % 8 == 0, "block must be a multiple of 8 samples");
+    const int NC = p->n_fft / 2;
+    {
+        const int key = NC * 16 + p->history_blocks;
+        const int ok[] = {256 * 16 + 1, 512 * 16 + 1, 1024 * 16 + 1, 2048 * 16 + 1, 1024 * 16 + 3, 2048 * 16 + 3, 2048 * 16 + 7, 4096 * 16 + 7};
+        bool found = false;
+        for (int k : ok) found = found || (k == key);
+        if (!found) return fail(JDSP_ERR_UNSUPPORTED, "fast-conv supports history_blocks 1 (n_fft 512..4096), 3 (2048, 4096) or 7 (4096, 8192)");
+    }
+    CU(cudaSetDevice(c->device));
+    jdsp_fastconv_state *st = new jdsp_fastconv_state();
+    st->p = *p;
+    st->n_sources = n_sources;
+    const long nfilt = p->shared_filter ? 1 : n_sources;
+    const long N = p->n_fft;
+    // transform the filters once, in double on the device, then keep bins 0..N/2 scaled by 1/(2N) in float
+    std::vector<jdsp_complex64> hin((size_t)nfilt * p->n_ears * N), hout((size_t)nfilt * p->n_ears * N);
+    memset(hin.data(), 0, hin.size() * sizeof(jdsp_complex64));
+    for (long f = 0; f < nfilt * p->n_ears; ++f)
+        for (int i = 0; i < p->n_taps && i < N; ++i) hin[f * N + i].re = taps[f * p->n_taps + i];
+    TRY(jdsp_fft_process(c, hin.data(), hout.data(), (int)N, 1, nfilt * p->n_ears));
+    std::vector<cf> hs((size_t)nfilt * p->n_ears * (NC + 1));
+    const double sc = 1.0 / (2.0 * (double)N);
+    for (long f = 0; f < nfilt * p->n_ears; ++f)
+        for (int k = 0; k <= NC; ++k) {
+            hs[f * (NC + 1) + k].x = (float)(hout[f * N + k].re * sc);
+            hs[f * (NC + 1) + k].y = (float)(hout[f * N + k].im * sc);
+        }
+    TRY(upload(c, hs, &st->d_hs));
+    CU(cudaMalloc((void **)&st->d_hist, (size_t)n_sources * p->history_blocks * p->block * sizeof(int16_t)));
+    TRY(jdsp_fastconv_state_reset(c, st));
+    *out = st;
+    return JDSP_OK;
+}
+}  // extern "C"
+
+template <int NC, int Q> static int launch_fastconv(jdsp_ctx *c, const FastconvArgs &a) {
+    using Geo = FastconvGeom<NC, Q>;
+    auto kfn = fastconv_kernel<NC, Q>;
+    const size_t smem = Geo::smem(a.sources_per_scene == 1 ? 1 : 2);
+    if (smem > 227 * 1024) return fail(JDSP_ERR_UNSUPPORTED, "fast-conv scene mixing does not fit shared memory at this size");
+    TRY(opt_in_smem(kfn, smem));
+    JDSP_LAUNCH_PTR(kfn, dim3(grid_for(c, a.n_scenes, 32)), dim3(Geo::NT), smem, c->stream, a);
+    return launch_check(c);
+}
+static int fastconv_run(jdsp_ctx *c, jdsp_fastconv_state *st, int sources_per_scene, const int16_t *d_in, long in_pitch, long n_blocks,
+                        int16_t *d_out, long out_pitch, float *d_out_f32, long f32_pitch, long *n_out_blocks) {
+    REQUIRE(c && st && d_in, "null argument");
+    REQUIRE(n_blocks >= 0, "negative n_blocks");
+    REQUIRE(sources_per_scene >= 1 && st->n_sources % sources_per_scene == 0, "sources_per_scene must divide n_sources");
+    const jdsp_fastconv_params &p = st->p;
+    const long skip = st->seen < p.history_blocks ? p.history_blocks - st->seen : 0;
+    const long emitted = n_blocks > skip ? n_blocks - skip : 0;
+    if (n_out_blocks) *n_out_blocks = emitted;
+    if (n_blocks == 0) return JDSP_OK;
+    REQUIRE(emitted == 0 || d_out, "d_out is null");
+    REQUIRE(in_pitch % 8 == 0 && out_pitch % 4 == 0 && f32_pitch % 4 == 0, "row pitches must keep rows 16-byte (in) / 8-byte (out) aligned");
+    REQUIRE((((uintptr_t)d_in) & 15) == 0 && (((uintptr_t)d_out) & 7) == 0 && (((uintptr_t)d_out_f32) & 15) == 0, "buffers must be 16-byte aligned");
+    CU(cudaSetDevice(c->device));
+    const int NC = p.n_fft / 2;
+    void *tw, *twr;
+    TRY(get_table(c, 0, NC, &tw));
+    TRY(get_table(c, 2, NC, &twr));
+    FastconvArgs a;
+    a.in = d_in; a.in_pitch = in_pitch; a.n_blocks = n_blocks; a.out = d_out; a.out_pitch = out_pitch;
+    a.out_f32 = d_out_f32; a.f32_pitch = f32_pitch; a.hs = st->d_hs; a.tw = (const cf *)tw; a.twr = (const float2 *)twr;
+    a.st_hist = st->d_hist; a.n_scenes = st->n_sources / sources_per_scene; a.sources_per_scene = sources_per_scene;
+    a.B = p.block; a.q = p.history_blocks; a.n_ears = p.n_ears; a.shared_filter = p.shared_filter; a.seen0 = st->seen;
+    int rc;
+    const int key = NC * 16 + p.history_blocks;
+    switch (key) {
+        case 256 * 16 + 1: rc = launch_fastconv<256, 1>(c, a); break;
+        case 512 * 16 + 1: rc = launch_fastconv<512, 1>(c, a); break;    // bench preset
+        case 1024 * 16 + 1: rc = launch_fastconv<1024, 1>(c, a); break;
+        case 2048 * 16 + 1: rc = launch_fastconv<2048, 1>(c, a); break;
+        case 1024 * 16 + 3: rc = launch_fastconv<1024, 3>(c, a); break;
+        case 2048 * 16 + 3: rc = launch_fastconv<2048, 3>(c, a); break;
+        case 2048 * 16 + 7: rc = launch_fastconv<2048, 7>(c, a); break;
+        case 4096 * 16 + 7: rc = launch_fastconv<4096, 7>(c, a); break;  // the reference program's literal constants
+        default: return fail(JDSP_ERR_UNSUPPORTED, "fast-conv supports history_blocks 1 (n_fft 512..4096), 3 (2048, 4096) or 7 (4096, 8192)");
+    }
+    if (rc == JDSP_OK) st->seen += n_blocks;
+    return rc;
+}
+
+extern "C" {
+int jdsp_fastconv_i16_dev(jdsp_ctx *c, jdsp_fastconv_state *st, const int16_t *d_in, long in_pitch, long n_blocks, int16_t *d_out,
+                          long out_pitch, float *d_out_f32, long f32_pitch, long *n_out_blocks) {
+    return fastconv_run(c, st, 1, d_in, in_pitch, n_blocks, d_out, out_pitch, d_out_f32, f32_pitch, n_out_blocks);
+}
+int jdsp_fastconv_mix_i16_dev(jdsp_ctx *c, jdsp_fastconv_state *st, int sources_per_scene, const int16_t *d_in, long in_pitch,
+                              long n_blocks, int16_t *d_out, long out_pitch, float *d_out_f32, long f32_pitch, long *n_out_blocks) {
+    return fastconv_run(c, st, sources_per_scene, d_in, in_pitch, n_blocks, d_out, out_pitch, d_out_f32, f32_pitch, n_out_blocks);
+}
+int jdsp_fastconv_i16(jdsp_ctx *c, const jdsp_fastconv_params *p, const double *taps, const int16_t *pcm, long n_samples, int16_t *out,
+                      long out_pitch, long *n_out_samples) {
+    REQUIRE(c && p && taps && pcm && out, "null argument");
+    REQUIRE(n_samples >= 0, "bad size");
+    const long B = p->block, nb = (n_samples + B - 1) / B;
+    const long n_out = nb > p->history_blocks ? (nb - p->history_blocks) * B : 0;
+    if (n_out_samples) *n_out_samples = n_out;
+    if (n_out == 0) return JDSP_OK;
+    REQUIRE(out_pitch >= n_out, "out_pitch too small");
+    jdsp_fastconv_params pp = *p;
+    pp.shared_filter = 1;
+    jdsp_fastconv_state *st = nullptr;
+    TRY(jdsp_fastconv_state_create(c, &pp, 1, taps, &st));
+    const long pitch = nb * B;
+    int16_t *d_in = nullptr, *d_out = nullptr;
+    int rc = JDSP_OK;
+    cudaError_t e = cudaMalloc((void **)&d_in, pitch * sizeof(int16_t));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_out, p->n_ears * pitch * sizeof(int16_t));
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_in, 0, pitch * sizeof(int16_t), c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, pcm, n_samples * sizeof(int16_t), cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) rc = fail(JDSP_ERR_CUDA, std::string("fastconv_i16 setup: ") + cudaGetErrorString(e));
+    if (rc == JDSP_OK) rc = apply_stale_tail(c, d_in, pitch, 1, n_samples, (int)B);
+    if (rc == JDSP_OK) rc = jdsp_fastconv_i16_dev(c, st, d_in, pitch, nb, d_out, pitch, nullptr, 0, nullptr);
+    if (rc == JDSP_OK) {
+        e = cudaMemcpy2DAsync(out, out_pitch * sizeof(int16_t), d_out, pitch * sizeof(int16_t), n_out * sizeof(int16_t), p->n_ears,
+                              cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = fail(JDSP_ERR_CUDA, std::string("fastconv_i16: ") + cudaGetErrorString(e));
+    }
+    cudaFree(d_in);
+    cudaFree(d_out);
+    jdsp_fastconv_state_destroy(c, st);
+    return rc;
+}
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// MFCC
+struct jdsp_mfcc_plan {
+    jdsp_mfcc_params p;
+    std::vector<double> weight;  // rgdFilterBank
+    std::vector<int32_t> chan;   // rgdFiBins
+    float *d_win_half = nullptr, *d_mel_w = nullptr, *d_dct = nullptr;
+    int *d_mel_start = nullptr;
+};
+
+extern "C" {
+int jdsp_mfcc_params_preset(const char *name, jdsp_mfcc_params *p) {
+    REQUIRE(name && p, "null argument");
+    memset(p, 0, sizeof(*p));
+    p->lifter = 22; p->preemph = 0.96; p->win_a0 = 0.54; p->win_a1 = 0.46; p->pi_literal = 3.141592;
+    if (!strcmp(name, "ref")) {          // MFCCFeatureExtraction_auto_version1.cpp:23-33
+        p->frame_len = 1024; p->hop = 512; p->n_fft = 1024; p->n_mel = 38; p->n_cep = 12; p->half_sr = 22050.0;
+    } else if (!strcmp(name, "mid")) {
+        p->frame_len = 512; p->hop = 256; p->n_fft = 512; p->n_mel = 26; p->n_cep = 13; p->half_sr = 8000.0;
+    } else if (!strcmp(name, "bench")) { // BASELINE.json config 4
+        p->frame_len = 400; p->hop = 160; p->n_fft = 512; p->n_mel = 26; p->n_cep = 13; p->half_sr = 8000.0;
+    } else {
+        return fail(JDSP_ERR_INVALID, "unknown MFCC preset (ref | mid | bench)");
+    }
+    return JDSP_OK;
+}
+int jdsp_mfcc_plan_destroy(jdsp_ctx *c, jdsp_mfcc_plan *pl) {
+    if (!pl) return JDSP_OK;
+    REQUIRE(c, "ctx is null");
+    cudaStreamSynchronize(c->stream);
+    cudaFree(pl->d_win_half); cudaFree(pl->d_mel_w); cudaFree(pl->d_dct); cudaFree(pl->d_mel_start);
+    delete pl;
+    return JDSP_OK;
+}
+int jdsp_mfcc_plan_create(jdsp_ctx *c, const jdsp_mfcc_params *p, jdsp_mfcc_plan **out) {
+    REQUIRE(c && p && out, "null argument");
+    if (p->n_fft != 512 && p->n_fft != 1024) return fail(JDSP_ERR_UNSUPPORTED, "MFCC supports n_fft 512 or 1024");
+    REQUIRE(p->frame_len >= 8 && p->frame_len <= p->n_fft && p->frame_len % 8 == 0, "frame_len must be a multiple of 8 and <= n_fft");
+    REQUIRE(p->hop >= 8 && p->hop % 8 == 0, "hop must be a multiple of 8 samples (16-byte bulk copies)");
+    REQUIRE(p->n_mel >= 1 && p->n_mel <= 64 && p->n_cep >= 1 && p->n_cep <= 16, "n_mel <= 64 and n_cep <= 16");
+    CU(cudaSetDevice(c->device));
+    jdsp_mfcc_plan *pl = new jdsp_mfcc_plan();
+    pl->p = *p;
+    const int C = p->n_mel, nbin = p->n_fft / 2, W = p->frame_len;
+    // M1 MelFilterBankInit (:118-152), same arithmetic, in double
+    std::vector<double> edge((size_t)C + 1);
+    const double unit = 1127.0 * log(1 + (p->half_sr / 700.0)) / (C + 1);
+    for (int i = 1; i <= C + 1; ++i) edge[i - 1] = 700 * (exp((unit * i) / 1127.0) - 1.0);
+    pl->weight.assign(nbin, 0.0);
+    pl->chan.assign(nbin, 0);
+    for (int i = 0, k = 0; i < nbin; ++i) {
+        if ((i / (double)(nbin - 1)) * p->half_sr > edge[k]) { if (k < C) k++; }  // at most one step per bin (:132-135)
+        pl->chan[i] = k;
+    }
+    for (int i = 0; i < nbin; ++i) {
+        const int k = pl->chan[i];
+        const double f = (i / (double)(nbin - 1)) * p->half_sr;
+        double w = (k == 0) ? (edge[k] - f) / (edge[k] - 0) : (edge[k] - f) / (edge[k] - edge[k - 1]);
+        if (w < 0) w = 0;
+        pl->weight[i] = w;
+    }
+    std::vector<float> mw(nbin);
+    for (int i = 0; i < nbin; ++i) mw[i] = (float)pl->weight[i];
+    std::vector<int> start((size_t)C + 2);
+    for (int v = 0; v <= C + 1; ++v) { int i = 0; while (i < nbin && pl->chan[i] < v) ++i; start[v] = i; }
+    // M4 DCT (:176-183) times M5 lifter (:185-192)
+    std::vector<float> dct((size_t)p->n_cep * C);
+    for (int i = 1; i <= p->n_cep; ++i) {
+        const double lift = 1 + 0.5 * p->lifter * sin(p->pi_literal * i / p->lifter);
+        for (int k = 1; k <= C; ++k) dct[(size_t)(i - 1) * C + (k - 1)] = (float)(sqrt(2.0 / C) * cos(p->pi_literal * i * (k - 0.5) / (double)C) * lift);
+    }
+    std::vector<float> wh(W);
+    for (int i = 0; i < W; ++i) wh[i] = (float)(0.5 * (p->win_a0 - p->win_a1 * cos(2 * p->pi_literal * i / (W - 1))));
+    TRY(upload(c, wh, &pl->d_win_half));
+    TRY(upload(c, mw, &pl->d_mel_w));
+    TRY(upload(c, dct, &pl->d_dct));
+    TRY(upload(c, start, &pl->d_mel_start));
+    *out = pl;
+    return JDSP_OK;
+}
+int jdsp_mfcc_plan_tables(jdsp_mfcc_plan *pl, double *weight, int32_t *chan) {
+    REQUIRE(pl && weight && chan, "null argument");
+    memcpy(weight, pl->weight.data(), pl->weight.size() * sizeof(double));
+    memcpy(chan, pl->chan.data(), pl->chan.size() * sizeof(int32_t));
+    return JDSP_OK;
+}
+}  // extern "C"
+
+template <int NC> static int launch_mfcc(jdsp_ctx *c, const MfccArgs &a) {
+    using Geo = MfccGeom<NC>;
+    auto kfn = mfcc_kernel<NC>;
+    const size_t smem = Geo::smem(a.frame_len, a.hop);
+    TRY(opt_in_smem(kfn, smem));
+    const long tiles = a.n_utts * ((a.n_frames + Geo::F - 1) / Geo::F);
+    JDSP_LAUNCH_PTR(kfn, dim3(grid_for(c, tiles, 32)), dim3(Geo::NT), smem, c->stream, a);
+    return launch_check(c);
+}
+
+extern "C" {
+int jdsp_mfcc_frames_i16_dev(jdsp_ctx *c, jdsp_mfcc_plan *pl, const int16_t *d_in, long in_pitch, long n_utts, long n_samples,
+                             float *d_feat, long feat_pitch, long *n_frames) {
+    REQUIRE(c && pl && d_in, "null argument");
+    const jdsp_mfcc_params &p = pl->p;
+    const long nf = n_samples >= p.frame_len ? (n_samples - p.frame_len) / p.hop + 1 : 0;
+    if (n_frames) *n_frames = nf;
+    if (nf == 0 || n_utts == 0) return JDSP_OK;
+    REQUIRE(d_feat, "d_feat is null");
+    REQUIRE(in_pitch % 8 == 0 && (((uintptr_t)d_in) & 15) == 0, "utterance rows must be 16-byte aligned (in_pitch % 8 == 0)");
+    REQUIRE(feat_pitch >= nf * p.n_cep, "feat_pitch too small");
+    CU(cudaSetDevice(c->device));
+    const int NC = p.n_fft / 2;
+    void *tw, *twr;
+    TRY(get_table(c, 0, NC, &tw));
+    TRY(get_table(c, 2, NC, &twr));
+    MfccArgs a;
+    a.in = d_in; a.in_pitch = in_pitch; a.n_utts = n_utts; a.n_samples = n_samples; a.n_frames = nf;
+    a.feat = d_feat; a.feat_pitch = feat_pitch; a.win_half = pl->d_win_half; a.tw = (const cf *)tw; a.twr = (const float2 *)twr;
+    a.mel_w = pl->d_mel_w; a.mel_start = pl->d_mel_start; a.dct = pl->d_dct;
+    a.frame_len = p.frame_len; a.hop = p.hop; a.n_mel = p.n_mel; a.n_cep = p.n_cep; a.preemph = (float)p.preemph;
+    return NC == 256 ? launch_mfcc<256>(c, a) : launch_mfcc<512>(c, a);
+}
+
+int jdsp_mfcc_program_i16(jdsp_ctx *c, const jdsp_mfcc_params *p, const int16_t *pcm, long n_samples, double *rows, long *n_rows) {
+    REQUIRE(c && p && pcm && rows, "null argument");
+    REQUIRE(p->frame_len == p->n_fft && p->n_fft == 2 * p->hop, "the program framing needs frame_len == n_fft == 2*hop");
+    const long H = p->hop, B = 2 * H, nb = (n_samples + B - 1) / B;
+    const long nr = nb > 0 ? 2 * nb - 1 : 0;
+    if (n_rows) *n_rows = nr;
+    if (nr == 0) return JDSP_OK;
+    jdsp_mfcc_plan *pl = nullptr;
+    TRY(jdsp_mfcc_plan_create(c, p, &pl));
+    const long total = H + nb * B;   // [hop zeros | blocks]  (:198,203-205)
+    int16_t *d_in = nullptr;
+    float *d_feat = nullptr;
+    std::vector<float> hfeat((size_t)(2 * nb) * p->n_cep);
+    int rc = JDSP_OK;
+    cudaError_t e = cudaMalloc((void **)&d_in, total * sizeof(int16_t));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_feat, hfeat.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_in, 0, total * sizeof(int16_t), c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_in + H, pcm, n_samples * sizeof(int16_t), cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) rc = fail(JDSP_ERR_CUDA, std::string("mfcc_program setup: ") + cudaGetErrorString(e));
+    if (rc == JDSP_OK) rc = apply_stale_tail(c, d_in + H, total, 1, n_samples, (int)B);
+    long nf = 0;
+    if (rc == JDSP_OK) rc = jdsp_mfcc_frames_i16_dev(c, pl, d_in, (total + 7) & ~7L, 1, total, d_feat, (long)hfeat.size(), &nf);
+    if (rc == JDSP_OK) {
+        e = cudaMemcpyAsync(hfeat.data(), d_feat, hfeat.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = fail(JDSP_ERR_CUDA, std::string("mfcc_program: ") + cudaGetErrorString(e));
+    }
+    if (rc == JDSP_OK) {
+        // first row skipped (:95-97), rows widened to the program's raw double[n_cep] format (:99)
+        for (long t = 1; t < nf; ++t)
+            for (int i = 0; i < p->n_cep; ++i) rows[(t - 1) * p->n_cep + i] = (double)hfeat[t * p->n_cep + i];
+    }
+    cudaFree(d_in);
+    cudaFree(d_feat);
+    jdsp_mfcc_plan_destroy(c, pl);
+    return rc;
+}
+}  // extern "C"
+

@@ -1,0 +1,292 @@
+// jdsp_stft.cu -- C ABI (include/jdsp.h), part 2: the round-trip and denoise pipelines (host-buffer and device-resident forms).
+#include "jdsp_host.hpp"
+#include "kernels_stft.cuh"
+
+// ---------------------------------------------------------------------------------------------------
+// Round trip
+template <int N> static int launch_roundtrip(jdsp_ctx *c, RoundtripArgs a) {
+    using Geo = RoundtripGeom<N>;
+    auto kfn = roundtrip_kernel<N>;
+    TRY(opt_in_smem(kfn, Geo::SMEM));
+    const long pairs = (a.n_blocks + 1) / 2;
+    const long tiles = a.n_streams * ((pairs + Geo::FPB - 1) / Geo::FPB);
+    JDSP_LAUNCH_PTR(kfn, dim3(grid_for(c, tiles, 16)), dim3(Geo::THREADS), Geo::SMEM, c->stream, a);
+    return launch_check(c);
+}
+
+extern "C" {
+int jdsp_roundtrip_i16_dev(jdsp_ctx *c, const int16_t *d_in, long in_pitch, int16_t *d_out, long out_pitch, float *d_out_f32,
+                           long f32_pitch, int n_fft, long n_streams, long n_blocks) {
+    REQUIRE(c && d_in && d_out, "null argument");
+    REQUIRE(n_streams >= 0 && n_blocks >= 0, "negative size");
+    REQUIRE(in_pitch % 2 == 0 && out_pitch % 2 == 0, "pitches must be even (4-byte aligned rows)");
+    if (n_streams == 0 || n_blocks == 0) return JDSP_OK;
+    CU(cudaSetDevice(c->device));
+    void *tw;
+    TRY(get_table(c, 0, n_fft, &tw));
+    RoundtripArgs a{d_in, in_pitch, d_out, out_pitch, d_out_f32, f32_pitch, (const cf *)tw, n_streams, n_blocks};
+    switch (n_fft) {
+        case 64: return launch_roundtrip<64>(c, a);
+        case 128: return launch_roundtrip<128>(c, a);
+        case 256: return launch_roundtrip<256>(c, a);
+        case 512: return launch_roundtrip<512>(c, a);
+        case 1024: return launch_roundtrip<1024>(c, a);
+        case 2048: return launch_roundtrip<2048>(c, a);
+        case 4096: return launch_roundtrip<4096>(c, a);
+        default: return fail(JDSP_ERR_UNSUPPORTED, "round trip supports n_fft = 64..4096 (power of two)");
+    }
+}
+int jdsp_roundtrip_i16(jdsp_ctx *c, const int16_t *pcm, long n_samples, int n_fft, int16_t *out, long *n_out) {
+    REQUIRE(c && pcm && out, "null argument");
+    REQUIRE(n_samples >= 0 && n_fft > 0, "bad size");
+    const long nb = (n_samples + n_fft - 1) / n_fft;
+    if (n_out) *n_out = nb * n_fft;
+    if (nb == 0) return JDSP_OK;
+    CU(cudaSetDevice(c->device));
+    const long pitch = nb * n_fft;
+    int16_t *d_in = nullptr, *d_out = nullptr;
+    CU(cudaMalloc((void **)&d_in, pitch * sizeof(int16_t)));
+    CU(cudaMalloc((void **)&d_out, pitch * sizeof(int16_t)));
+    int rc = JDSP_OK;
+    do {
+        if (cudaMemsetAsync(d_in, 0, pitch * sizeof(int16_t), c->stream) != cudaSuccess ||
+            cudaMemcpyAsync(d_in, pcm, n_samples * sizeof(int16_t), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { rc = fail(JDSP_ERR_CUDA, "H2D copy failed"); break; }
+        if ((rc = apply_stale_tail(c, d_in, pitch, 1, n_samples, n_fft)) != JDSP_OK) break;
+        if ((rc = jdsp_roundtrip_i16_dev(c, d_in, pitch, d_out, pitch, nullptr, 0, n_fft, 1, nb)) != JDSP_OK) break;
+        if (cudaMemcpyAsync(out, d_out, pitch * sizeof(int16_t), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { rc = fail(JDSP_ERR_CUDA, "D2H copy failed"); break; }
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = fail(JDSP_ERR_CUDA, std::string("roundtrip: ") + cudaGetErrorString(e));
+    } while (0);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    return rc;
+}
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// Denoise
+struct jdsp_denoise_state {
+    jdsp_denoise_params p;
+    long n_streams = 0;
+    long seen = 0;  // blocks consumed so far (identical for every stream)
+    int32_t *d_seen = nullptr, *d_run = nullptr, *d_pub = nullptr;
+    float *d_avg = nullptr, *d_ns = nullptr, *d_ola = nullptr;
+    int16_t *d_prev = nullptr;
+    float *d_win_half = nullptr;
+    double *d_win_vad = nullptr;
+};
+
+extern "C" {
+int jdsp_denoise_params_preset(const char *name, int mode, jdsp_denoise_params *p) {
+    REQUIRE(name && p, "null argument");
+    REQUIRE(mode == JDSP_DENOISE_SS || mode == JDSP_DENOISE_WIENER, "mode must be JDSP_DENOISE_SS or JDSP_DENOISE_WIENER");
+    memset(p, 0, sizeof(*p));
+    p->mode = mode;
+    p->noise_frames = 10;
+    p->pi_literal = 3.141592;
+    p->energy_thr = 700.0;
+    if (!strcmp(name, "ref")) {          // SpectralSubtraction_final.cpp:48-56,226
+        p->n_fft = 1024; p->hop = 512; p->zcr_thr = 200; p->win_a0 = 0.54; p->win_a1 = 0.46;
+    } else if (!strcmp(name, "bench")) { // BASELINE.json config 2
+        p->n_fft = 512; p->hop = 256; p->zcr_thr = 64; p->win_a0 = 0.5; p->win_a1 = 0.5;
+    } else {
+        return fail(JDSP_ERR_INVALID, "unknown denoise preset (ref | bench)");
+    }
+    return JDSP_OK;
+}
+
+int jdsp_denoise_state_reset(jdsp_ctx *c, jdsp_denoise_state *st) {
+    REQUIRE(c && st, "null argument");
+    const long S = st->n_streams, NC = st->p.n_fft / 2, H = st->p.hop;
+    CU(cudaMemsetAsync(st->d_seen, 0, S * sizeof(int32_t), c->stream));
+    CU(cudaMemsetAsync(st->d_run, 0, S * sizeof(int32_t), c->stream));
+    CU(cudaMemsetAsync(st->d_pub, 0, S * sizeof(int32_t), c->stream));
+    CU(cudaMemsetAsync(st->d_avg, 0, S * (NC + 1) * sizeof(float), c->stream));
+    CU(cudaMemsetAsync(st->d_ns, 0, S * (NC + 1) * sizeof(float), c->stream));
+    CU(cudaMemsetAsync(st->d_ola, 0, S * H * sizeof(float), c->stream));
+    CU(cudaMemsetAsync(st->d_prev, 0, S * H * sizeof(int16_t), c->stream));
+    st->seen = 0;
+    return JDSP_OK;
+}
+int jdsp_denoise_state_destroy(jdsp_ctx *c, jdsp_denoise_state *st) {
+    if (!st) return JDSP_OK;
+    REQUIRE(c, "ctx is null");
+    cudaStreamSynchronize(c->stream);
+    cudaFree(st->d_seen); cudaFree(st->d_run); cudaFree(st->d_pub); cudaFree(st->d_avg); cudaFree(st->d_ns);
+    cudaFree(st->d_ola); cudaFree(st->d_prev); cudaFree(st->d_win_half); cudaFree(st->d_win_vad);
+    delete st;
+    return JDSP_OK;
+}
+int jdsp_denoise_state_create(jdsp_ctx *c, const jdsp_denoise_params *p, long n_streams, jdsp_denoise_state **out) {
+    REQUIRE(c && p && out, "null argument");
+    REQUIRE(n_streams >= 1, "n_streams must be >= 1");
+    REQUIRE(p->n_fft == 2 * p->hop, "n_fft must equal 2*hop (the reference's 50% overlap)");
+    if (p->n_fft != 512 && p->n_fft != 1024) return fail(JDSP_ERR_UNSUPPORTED, "denoise supports n_fft 512 or 1024");
+    REQUIRE(p->mode == 0 || p->mode == 1, "bad mode");
+    REQUIRE(p->noise_frames >= 2, "noise_frames must be >= 2");
+    CU(cudaSetDevice(c->device));
+    jdsp_denoise_state *st = new jdsp_denoise_state();
+    st->p = *p;
+    st->n_streams = n_streams;
+    const long S = n_streams, NC = p->n_fft / 2, H = p->hop, N = p->n_fft;
+    CU(cudaMalloc((void **)&st->d_seen, S * sizeof(int32_t)));
+    CU(cudaMalloc((void **)&st->d_run, S * sizeof(int32_t)));
+    CU(cudaMalloc((void **)&st->d_pub, S * sizeof(int32_t)));
+    CU(cudaMalloc((void **)&st->d_avg, S * (NC + 1) * sizeof(float)));
+    CU(cudaMalloc((void **)&st->d_ns, S * (NC + 1) * sizeof(float)));
+    CU(cudaMalloc((void **)&st->d_ola, S * H * sizeof(float)));
+    CU(cudaMalloc((void **)&st->d_prev, S * H * sizeof(int16_t)));
+    // window in double with the program's PI literal (:226); the kernel takes 0.5*w in float for the transform
+    // and w[H..N) in double for the bit-exact VAD (:131)
+    std::vector<float> wh((size_t)N);
+    std::vector<double> wv((size_t)H);
+    for (long i = 0; i < N; ++i) {
+        const double w = p->win_a0 - p->win_a1 * cos(2 * p->pi_literal * i / (N - 1));
+        wh[i] = (float)(0.5 * w);
+        if (i >= H) wv[i - H] = w;
+    }
+    TRY(upload(c, wh, &st->d_win_half));
+    TRY(upload(c, wv, &st->d_win_vad));
+    TRY(jdsp_denoise_state_reset(c, st));
+    *out = st;
+    return JDSP_OK;
+}
+}  // extern "C"
+
+template <int NC, int F>
+static int launch_denoise(jdsp_ctx *c, const DenoiseArgs &a, int mode) {
+    using Geo = DenoiseGeom<NC, F>;
+    const unsigned grid = grid_for(c, a.n_streams, 32);
+    if (mode == 0) {
+        auto kfn = denoise_kernel<NC, F, 0>;
+        TRY(opt_in_smem(kfn, Geo::SMEM));
+        JDSP_LAUNCH_PTR(kfn, dim3(grid), dim3(Geo::NT), Geo::SMEM, c->stream, a);
+    } else {
+        auto kfn = denoise_kernel<NC, F, 1>;
+        TRY(opt_in_smem(kfn, Geo::SMEM));
+        JDSP_LAUNCH_PTR(kfn, dim3(grid), dim3(Geo::NT), Geo::SMEM, c->stream, a);
+    }
+    return launch_check(c);
+}
+
+// stream0/n: the slice of the state's streams this launch covers
+static int denoise_launch_slice(jdsp_ctx *c, jdsp_denoise_state *st, cudaStream_t stream, long stream0, long n, const int16_t *d_in,
+                                long in_pitch, long n_blocks, int16_t *d_out, long out_pitch, float *d_out_f32, long f32_pitch,
+                                uint8_t *d_vad) {
+    const jdsp_denoise_params &p = st->p;
+    const long NC = p.n_fft / 2, H = p.hop;
+    void *tw, *twr;
+    TRY(get_table(c, 0, (int)NC, &tw));
+    TRY(get_table(c, 2, (int)NC, &twr));
+    DenoiseArgs a;
+    a.in = d_in; a.in_pitch = in_pitch; a.n_blocks = n_blocks;
+    a.out = d_out; a.out_pitch = out_pitch; a.out_f32 = d_out_f32; a.f32_pitch = f32_pitch; a.vad = d_vad;
+    a.win_half = st->d_win_half; a.win_vad = st->d_win_vad; a.tw = (const cf *)tw; a.twr = (const float2 *)twr;
+    a.st_seen = st->d_seen + stream0; a.st_run = st->d_run + stream0; a.st_pub = st->d_pub + stream0;
+    a.st_avg = st->d_avg + stream0 * (NC + 1); a.st_ns = st->d_ns + stream0 * (NC + 1);
+    a.st_prev = st->d_prev + stream0 * H; a.st_ola = st->d_ola + stream0 * H;
+    a.n_streams = n; a.zcr_thr = p.zcr_thr; a.noise_frames = p.noise_frames; a.energy_thr = p.energy_thr;
+    a.skip_blocks = st->seen < 2 ? 2 - st->seen : 0;
+    cudaStream_t saved = c->stream;
+    c->stream = stream;
+    int rc = (p.n_fft == 512) ? launch_denoise<256, 8>(c, a, p.mode) : launch_denoise<512, 4>(c, a, p.mode);
+    c->stream = saved;
+    return rc;
+}
+
+extern "C" {
+int jdsp_denoise_i16_dev(jdsp_ctx *c, jdsp_denoise_state *st, const int16_t *d_in, long in_pitch, long n_blocks, int16_t *d_out,
+                         long out_pitch, float *d_out_f32, long f32_pitch, uint8_t *d_vad, long *n_out_blocks) {
+    REQUIRE(c && st && d_in, "null argument");
+    REQUIRE(n_blocks >= 0, "negative n_blocks");
+    const long skip = st->seen < 2 ? 2 - st->seen : 0;
+    const long emitted = n_blocks > skip ? n_blocks - skip : 0;
+    if (n_out_blocks) *n_out_blocks = emitted;
+    if (n_blocks == 0) return JDSP_OK;
+    REQUIRE(emitted == 0 || d_out, "d_out is null");
+    REQUIRE(in_pitch % 8 == 0 && out_pitch % 8 == 0 && f32_pitch % 4 == 0, "row pitches must keep rows 16-byte aligned");
+    REQUIRE((((uintptr_t)d_in) & 15) == 0 && (((uintptr_t)d_out) & 15) == 0 && (((uintptr_t)d_out_f32) & 15) == 0, "buffers must be 16-byte aligned");
+    CU(cudaSetDevice(c->device));
+    TRY(denoise_launch_slice(c, st, c->stream, 0, st->n_streams, d_in, in_pitch, n_blocks, d_out, out_pitch, d_out_f32, f32_pitch, d_vad));
+    st->seen += n_blocks;
+    return JDSP_OK;
+}
+
+int jdsp_denoise_publish_counts(jdsp_ctx *c, jdsp_denoise_state *st, int32_t *counts) {
+    REQUIRE(c && st && counts, "null argument");
+    CU(cudaMemcpyAsync(counts, st->d_pub, st->n_streams * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return JDSP_OK;
+}
+
+int jdsp_denoise_i16(jdsp_ctx *c, const jdsp_denoise_params *p, const int16_t *in, long in_pitch, long n_streams, long n_samples,
+                     int16_t *out, long out_pitch, long *n_out_samples) {
+    REQUIRE(c && p && in && out, "null argument");
+    REQUIRE(n_streams >= 1 && n_samples >= 0, "bad size");
+    const long H = p->hop;
+    REQUIRE(H > 0, "bad hop");
+    const long nb = (n_samples + H - 1) / H;
+    const long n_out = nb > 2 ? (nb - 2) * H : 0;
+    if (n_out_samples) *n_out_samples = n_out;
+    if (nb == 0) return JDSP_OK;
+    CU(cudaSetDevice(c->device));
+    // per-stream state objects are cached per (params, n_streams) and reset, not re-created, on every call
+    jdsp_denoise_state *st = nullptr;
+    for (auto *cand : c->denoise_cache)
+        if (cand->n_streams == n_streams && !memcmp(&cand->p, p, sizeof(*p))) st = cand;
+    if (!st) {
+        TRY(jdsp_denoise_state_create(c, p, n_streams, &st));
+        if (c->denoise_cache.size() >= 4) { jdsp_denoise_state_destroy(c, c->denoise_cache.front()); c->denoise_cache.erase(c->denoise_cache.begin()); }
+        c->denoise_cache.push_back(st);
+    } else {
+        TRY(jdsp_denoise_state_reset(c, st));
+    }
+    // chunks of streams ride three CUDA streams so H2D, compute and D2H of neighbouring chunks overlap
+    const long row_in = nb * H, row_out = n_out > 0 ? n_out : 8;
+    long chunk = (128L << 20) / (long)(row_in * sizeof(int16_t));
+    if (chunk < 1) chunk = 1;
+    if (chunk > n_streams) chunk = n_streams;
+    const int nslots = (n_streams + chunk - 1) / chunk > 1 ? 3 : 1;
+    TRY(ensure_workspace(c, (size_t)chunk * row_in * sizeof(int16_t), (size_t)chunk * row_out * sizeof(int16_t), nslots));
+    int16_t *d_in[3], *d_out[3];
+    for (int i = 0; i < 3; ++i) { d_in[i] = (int16_t *)c->ws_in[i]; d_out[i] = (int16_t *)c->ws_out[i]; }
+    int rc = JDSP_OK;
+    cudaError_t e = cudaSuccess;
+    {
+        cudaStreamSynchronize(c->stream);  // state reset done before the pipe streams touch it
+        int slot = 0;
+        for (long s0 = 0; s0 < n_streams && rc == JDSP_OK; s0 += chunk, slot = (slot + 1) % nslots) {
+            const long ns = n_streams - s0 < chunk ? n_streams - s0 : chunk;
+            cudaStream_t q = c->pipe[slot];
+            if (in_pitch == row_in && n_samples == row_in)   // contiguous rows: one linear copy (full PCIe rate, overlaps with D2H)
+                e = cudaMemcpyAsync(d_in[slot], in + s0 * in_pitch, (size_t)ns * row_in * sizeof(int16_t), cudaMemcpyHostToDevice, q);
+            else
+                e = cudaMemcpy2DAsync(d_in[slot], row_in * sizeof(int16_t), in + s0 * in_pitch, in_pitch * sizeof(int16_t),
+                                      n_samples * sizeof(int16_t), ns, cudaMemcpyHostToDevice, q);
+            if (e != cudaSuccess) { rc = fail(JDSP_ERR_CUDA, std::string("denoise_i16 H2D: ") + cudaGetErrorString(e)); break; }
+            if (n_samples % H) {
+                cudaStream_t saved = c->stream; c->stream = q;
+                rc = apply_stale_tail(c, d_in[slot], row_in, ns, n_samples, (int)H);
+                c->stream = saved;
+                if (rc != JDSP_OK) break;
+            }
+            rc = denoise_launch_slice(c, st, q, s0, ns, d_in[slot], row_in, nb, d_out[slot], row_out, nullptr, 0, nullptr);
+            if (rc != JDSP_OK) break;
+            if (n_out > 0) {
+                if (out_pitch == row_out)
+                    e = cudaMemcpyAsync(out + s0 * out_pitch, d_out[slot], (size_t)ns * row_out * sizeof(int16_t), cudaMemcpyDeviceToHost, q);
+                else
+                    e = cudaMemcpy2DAsync(out + s0 * out_pitch, out_pitch * sizeof(int16_t), d_out[slot], row_out * sizeof(int16_t),
+                                          n_out * sizeof(int16_t), ns, cudaMemcpyDeviceToHost, q);
+                if (e != cudaSuccess) { rc = fail(JDSP_ERR_CUDA, std::string("denoise_i16 D2H: ") + cudaGetErrorString(e)); break; }
+            }
+        }
+        for (int i = 0; i < nslots; ++i) {
+            e = cudaStreamSynchronize(c->pipe[i]);
+            if (e != cudaSuccess && rc == JDSP_OK) rc = fail(JDSP_ERR_CUDA, std::string("denoise_i16: ") + cudaGetErrorString(e));
+        }
+    }
+    return rc;
+}
+}  // extern "C"
+
