@@ -278,6 +278,34 @@ JDSP_DEV void group_fft_regtw(cx<T> (&reg)[E], int t, cx<T> *buf, const cx<T> (&
     dftR<E, INV>(reg);
 }
 
+// Two-pass transform (NC = E*E) whose second-pass twiddles W_NC^(i*t) are rebuilt per transform from the four seeds
+// i = 1, 2, 4, 8 (11 complex products, depth <= 3: ~2e-7 relative) instead of 15 table loads.  For kernels whose binding
+// resource is the shared-memory data pipe (the 64-bit loads of a table that both half warps read cost two wavefronts each),
+// this trades 11 wavefront pairs for 22 packed-FMA issue slots per transform.
+template <typename T, int NC, int E, bool INV, int SYNC>
+JDSP_DEV void group_fft_seedtw(cx<T> (&reg)[E], int t, cx<T> *buf, const cx<T> *__restrict__ tw) {
+    static_assert(NC == E * E && E == 16, "seeded twiddles are for the 16 x 16 two-pass case");
+    dftR<E, INV>(reg);
+    fft_pass_store<T, NC, E, E, 1>(reg, t, buf);
+    const cx<T> *twp = tw + TwLayout<NC, E>::offset(E) + t;
+    const cx<T> w1 = twp[0], w2 = twp[E], w4 = twp[3 * E], w8 = twp[7 * E];
+    group_sync<SYNC>();
+    fft_load_regs<T, NC, E>(reg, t, buf);
+    reg[1] = cmul<INV>(reg[1], w1); reg[2] = cmul<INV>(reg[2], w2); reg[4] = cmul<INV>(reg[4], w4); reg[8] = cmul<INV>(reg[8], w8);
+    const cx<T> w3 = cmul<false>(w1, w2), w5 = cmul<false>(w1, w4), w6 = cmul<false>(w2, w4);
+    reg[3] = cmul<INV>(reg[3], w3); reg[5] = cmul<INV>(reg[5], w5); reg[6] = cmul<INV>(reg[6], w6);
+    const cx<T> w7 = cmul<false>(w3, w4);
+    reg[7] = cmul<INV>(reg[7], w7);
+    reg[9] = cmul<INV>(reg[9], cmul<false>(w1, w8));
+    reg[10] = cmul<INV>(reg[10], cmul<false>(w2, w8));
+    reg[11] = cmul<INV>(reg[11], cmul<false>(w3, w8));
+    reg[12] = cmul<INV>(reg[12], cmul<false>(w4, w8));
+    reg[13] = cmul<INV>(reg[13], cmul<false>(w5, w8));
+    reg[14] = cmul<INV>(reg[14], cmul<false>(w6, w8));
+    reg[15] = cmul<INV>(reg[15], cmul<false>(w7, w8));
+    dftR<E, INV>(reg);
+}
+
 // ---- small numeric helpers ---------------------------------------------------------------------------
 // (short)(double) of the reference: truncate toward zero, keep the low 16 bits
 JDSP_DEV int16_t trunc16(float v) { return (int16_t)__float2int_rz(v); }

@@ -1,6 +1,7 @@
 // jdsp_stft.cu -- C ABI (include/jdsp.h), part 2: the round-trip and denoise pipelines (host-buffer and device-resident forms).
 #include "jdsp_host.hpp"
 #include "kernels_stft.cuh"
+#include "kernels_stream.cuh"
 
 // ---------------------------------------------------------------------------------------------------
 // Round trip
@@ -169,6 +170,27 @@ static int launch_denoise(jdsp_ctx *c, const DenoiseArgs &a, int mode) {
     return launch_check(c);
 }
 
+// One thread group per stream (kernels_stream.cuh): the default.  JDSP_DENOISE_KERNEL=tile selects the CTA-per-stream kernel.
+template <int NC, int E = 16>
+static int launch_denoise_stream(jdsp_ctx *c, const DenoiseArgs &a, int mode) {
+    using Geo = StreamGeom<NC, E>;
+    const unsigned grid = (unsigned)((a.n_streams + Geo::GPC - 1) / Geo::GPC);
+    if (mode == 0) {
+        auto kfn = denoise_stream_kernel<NC, 0, E>;
+        TRY(opt_in_smem(kfn, Geo::SMEM));
+        JDSP_LAUNCH_PTR(kfn, dim3(grid), dim3(Geo::NT), Geo::SMEM, c->stream, a);
+    } else {
+        auto kfn = denoise_stream_kernel<NC, 1, E>;
+        TRY(opt_in_smem(kfn, Geo::SMEM));
+        JDSP_LAUNCH_PTR(kfn, dim3(grid), dim3(Geo::NT), Geo::SMEM, c->stream, a);
+    }
+    return launch_check(c);
+}
+static bool denoise_use_tile_kernel() {
+    const char *e = getenv("JDSP_DENOISE_KERNEL");
+    return e && !strcmp(e, "tile");
+}
+
 // stream0/n: the slice of the state's streams this launch covers
 static int denoise_launch_slice(jdsp_ctx *c, jdsp_denoise_state *st, cudaStream_t stream, long stream0, long n, const int16_t *d_in,
                                 long in_pitch, long n_blocks, int16_t *d_out, long out_pitch, float *d_out_f32, long f32_pitch,
@@ -189,7 +211,15 @@ static int denoise_launch_slice(jdsp_ctx *c, jdsp_denoise_state *st, cudaStream_
     a.skip_blocks = st->seen < 2 ? 2 - st->seen : 0;
     cudaStream_t saved = c->stream;
     c->stream = stream;
-    int rc = (p.n_fft == 512) ? launch_denoise<256, 8>(c, a, p.mode) : launch_denoise<512, 4>(c, a, p.mode);
+    int rc;
+    if (denoise_use_tile_kernel()) rc = (p.n_fft == 512) ? launch_denoise<256, 8>(c, a, p.mode) : launch_denoise<512, 4>(c, a, p.mode);
+    else if (p.n_fft == 512 && getenv("JDSP_STREAM_E8")) {   // experiment: a warp per stream, 8 points per thread
+        void *tw8;
+        TRY(get_table(c, 5, (int)NC, &tw8));
+        a.tw = (const cf *)tw8;
+        rc = launch_denoise_stream<256, 8>(c, a, p.mode);
+    }
+    else rc = (p.n_fft == 512) ? launch_denoise_stream<256>(c, a, p.mode) : launch_denoise_stream<512>(c, a, p.mode);
     c->stream = saved;
     return rc;
 }

@@ -23,6 +23,7 @@
 #define __forceinline__ inline __attribute__((always_inline))
 #define __restrict__ __restrict
 #define __launch_bounds__(...)
+#define __maxnreg__(...)
 #define __shared__ static
 #define __constant__ static
 #define __align__(n) __attribute__((aligned(n)))

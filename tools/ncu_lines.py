@@ -13,8 +13,9 @@ which = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 with tempfile.TemporaryDirectory() as d:
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "jeicyboodsp_b200", "libjdsp.so")], cwd=d, check=True, stdout=subprocess.DEVNULL)
-    cub = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
-    dis = subprocess.run(["nvdisasm", "--print-line-info", "--print-code", os.path.join(d, cub)], capture_output=True, text=True).stdout
+    dis = ""
+    for cub in sorted(f for f in os.listdir(d) if f.endswith(".cubin")):   # one cubin per translation unit
+        dis += subprocess.run(["nvdisasm", "--print-line-info", "--print-code", os.path.join(d, cub)], capture_output=True, text=True).stdout
 # address -> line
 sec, line, amap = None, None, {}
 for ln in dis.splitlines():
