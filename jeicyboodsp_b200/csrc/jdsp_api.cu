@@ -91,6 +91,21 @@ static int launch_c2c_small(jdsp_ctx *c, const cx<T> *in, cx<T> *out, long batch
     JDSP_LAUNCH_PTR(kfn, dim3(grid_for(c, tiles, 16)), dim3(Geo::THREADS), smem, c->stream, in, out, batch, tw, (T)1);
     return launch_check(c);
 }
+// fp32 N = 2048..8192: persistent CTAs, next transform bulk-prefetched (JDSP_FFT_NO_PIPE=1 selects the plain kernel)
+template <int N, bool INV>
+static int launch_c2c_pipe(jdsp_ctx *c, const cx<float> *in, cx<float> *out, long batch, const cx<float> *tw) {
+    using Geo = FftPipeGeom<N>;
+    auto kfn = fft_c2c_pipe_kernel<N, INV>;
+    TRY(opt_in_smem(kfn, Geo::SMEM));
+    int per_sm = 1;
+#ifndef JDSP_EMUL
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, Geo::THREADS, Geo::SMEM));
+    if (per_sm < 1) return fail(JDSP_ERR_CUDA, "pipelined FFT kernel does not fit an SM");
+#endif
+    JDSP_LAUNCH_PTR(kfn, dim3(grid_for(c, batch, per_sm)), dim3(Geo::THREADS), Geo::SMEM, c->stream, in, out, batch, tw, 1.0f);
+    return launch_check(c);
+}
+
 template <typename T, int N1, int N2, bool INV>
 static int launch_c2c_fourstep(jdsp_ctx *c, const cx<T> *in, cx<T> *out, long batch, int tkind) {
     constexpr int CT = sizeof(T) == 4 ? 32 : 16, RT = sizeof(T) == 4 ? 32 : 16;
@@ -164,13 +179,16 @@ template <typename T, bool INV>
 static int fft_dispatch(jdsp_ctx *c, const cx<T> *in, cx<T> *out, int n, long batch) {
     const int tkind = sizeof(T) == 4 ? 0 : 1;
     void *tw = nullptr;
-    if (n <= 8192) TRY(get_table(c, tkind, n, &tw));
+    if (n <= 8192 || (n == 16384 && sizeof(T) == 4 && getenv("JDSP_FFT_ONCHIP16K"))) TRY(get_table(c, tkind, n, &tw));
     const cx<T> *t = (const cx<T> *)tw;
     switch (n) {
 #define SMALL(NN) case NN: return launch_c2c_small<T, NN, INV>(c, in, out, batch, t);
-        SMALL(2) SMALL(4) SMALL(8) SMALL(16) SMALL(32) SMALL(64) SMALL(128) SMALL(256) SMALL(512) SMALL(1024) SMALL(2048) SMALL(4096) SMALL(8192)
+#define PIPE(NN) case NN: if constexpr (sizeof(T) == 4) { if (!getenv("JDSP_FFT_NO_PIPE")) return launch_c2c_pipe<NN, INV>(c, (const cx<float> *)in, (cx<float> *)out, batch, (const cx<float> *)t); } return launch_c2c_small<T, NN, INV>(c, in, out, batch, t);
+        SMALL(2) SMALL(4) SMALL(8) SMALL(16) SMALL(32) SMALL(64) SMALL(128) SMALL(256) SMALL(512) SMALL(1024) PIPE(2048) PIPE(4096) PIPE(8192)
+#undef PIPE
 #undef SMALL
         case 16384:
+            if constexpr (sizeof(T) == 4) { if (getenv("JDSP_FFT_ONCHIP16K")) return launch_c2c_small<T, 16384, INV>(c, in, out, batch, t); }
             if constexpr (sizeof(T) == 4) { if (getenv("JDSP_FFT_FUSED")) return launch_c2c_fused<64, 256, INV>(c, in, out, batch); }
             return launch_c2c_fourstep<T, 64, 256, INV>(c, in, out, batch, tkind);
         case 32768:

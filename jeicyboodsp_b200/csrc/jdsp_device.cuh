@@ -306,6 +306,50 @@ JDSP_DEV void group_fft_seedtw(cx<T> (&reg)[E], int t, cx<T> *buf, const cx<T> *
     dftR<E, INV>(reg);
 }
 
+// ================================================================================================
+// Asynchronous bulk staging (TMA 1-D bulk copy, cp.async.bulk -> UBLKCP in SASS) of frame tiles into
+// shared memory, completion tracked by an mbarrier.  One elected thread issues; every thread waits.
+// ================================================================================================
+JDSP_DEV void mbar_init(uint64_t *bar, int count) {
+#ifdef JDSP_EMUL
+    *bar = 0; (void)count;
+#else
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+}
+JDSP_DEV void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+#ifdef JDSP_EMUL
+    (void)bytes; *bar += 1;   // emulated bulk copies complete at issue (no yield between this and the copies): count phases
+#else
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+#endif
+}
+JDSP_DEV void bulk_g2s(void *smem_dst, const void *gsrc, unsigned bytes, uint64_t *bar) {
+#ifdef JDSP_EMUL
+    memcpy(smem_dst, gsrc, bytes); (void)bar;
+#else
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+#endif
+}
+JDSP_DEV void mbar_wait(uint64_t *bar, unsigned parity) {
+#ifdef JDSP_EMUL
+    while (((*bar) & 1u) == parity) jdsp_emul::yield();   // same rule as try_wait.parity: done once the phase parity has flipped
+#else
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(a), "r"(parity) : "memory");
+#endif
+}
+
 // ---- small numeric helpers ---------------------------------------------------------------------------
 // (short)(double) of the reference: truncate toward zero, keep the low 16 bits
 JDSP_DEV int16_t trunc16(float v) { return (int16_t)__float2int_rz(v); }

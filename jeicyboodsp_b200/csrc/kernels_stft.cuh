@@ -129,50 +129,6 @@ __global__ void __launch_bounds__(RoundtripGeom<N>::THREADS) roundtrip_kernel(Ro
 }
 
 // ================================================================================================
-// Asynchronous bulk staging (TMA 1-D bulk copy, cp.async.bulk -> UBLKCP in SASS) of frame tiles into
-// shared memory, completion tracked by an mbarrier.  One elected thread issues; every thread waits.
-// ================================================================================================
-JDSP_DEV void mbar_init(uint64_t *bar, int count) {
-#ifdef JDSP_EMUL
-    *bar = 0; (void)count;
-#else
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-#endif
-}
-JDSP_DEV void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
-#ifdef JDSP_EMUL
-    (void)bar; (void)bytes;
-#else
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
-#endif
-}
-JDSP_DEV void bulk_g2s(void *smem_dst, const void *gsrc, unsigned bytes, uint64_t *bar) {
-#ifdef JDSP_EMUL
-    memcpy(smem_dst, gsrc, bytes); (void)bar;
-#else
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     (unsigned)__cvta_generic_to_shared(smem_dst)),
-                 "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
-                 : "memory");
-#endif
-}
-JDSP_DEV void mbar_wait(uint64_t *bar, unsigned parity) {
-#ifdef JDSP_EMUL
-    (void)bar; (void)parity;
-#else
-    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(a), "r"(parity) : "memory");
-#endif
-}
-
-// ================================================================================================
 // Denoise.  One CTA walks one stream in tiles of F consecutive frames (hop H = NC, frame N = 2*NC,
 // packed-real transform length NC).  Thread groups of G = NC/16 threads own one frame each for the
 // transforms; for the per-bin stage every thread owns fixed bin pairs (k, NC-k) across ALL frames so the
