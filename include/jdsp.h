@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define JDSP_ABI_VERSION 1
+#define JDSP_ABI_VERSION 2
 
 #define JDSP_OK 0
 #define JDSP_ERR_INVALID (-1)     /* bad argument */
@@ -136,6 +136,35 @@ int jdsp_denoise_i16(jdsp_ctx *ctx, const jdsp_denoise_params *p, const int16_t 
 /* number of noise-spectrum publishes so far per stream (host array of n_streams) -- harness check
  * that the noise path actually fired */
 int jdsp_denoise_publish_counts(jdsp_ctx *ctx, jdsp_denoise_state *st, int32_t *counts);
+
+/* ---- P1: pitch by FFT autocorrelation (CalcPitch, PitchEstimation_method1.cpp:69-116) ---------- */
+typedef struct {
+    int32_t n_fft;    /* FFT_PROCESSING_SIZE (:26): 1024                                                  */
+    int32_t block;    /* BLOCK_SIZE == KEEP_LENGTH (:25,27): 512.  frame = [previous block | block], no window */
+    int32_t min_lag;  /* the scan stops above this lag (:101): 100                                          */
+    int32_t reserved;
+    double fs;        /* DEFAULT_SAMPLINGRATE (:28): pitch = fs / arg (left to the caller, :109)            */
+} jdsp_pitch_params;
+int jdsp_pitch_params_preset(const char *name /* "ref" */, jdsp_pitch_params *p);
+/* Replaces `static short rgssKeepBuffer[KEEP_LENGTH]` (:73): the previous block of every stream. */
+typedef struct jdsp_pitch_state jdsp_pitch_state;
+int jdsp_pitch_state_create(jdsp_ctx *ctx, const jdsp_pitch_params *p, long n_streams, jdsp_pitch_state **st);
+int jdsp_pitch_state_reset(jdsp_ctx *ctx, jdsp_pitch_state *st);
+int jdsp_pitch_state_destroy(jdsp_ctx *ctx, jdsp_pitch_state *st);
+/*
+ * One call = CalcPitch over `n_blocks` consecutive whole blocks of every stream.
+ *   d_in   [stream][n_blocks*block], row pitch in_pitch (even).
+ *   d_arg  [stream][n_blocks] int32: the smallest lag in (min_lag, block) attaining the maximum of the circular
+ *          autocorrelation of the frame (the reference's downward `>=` scan, :101-108), decided on EXACT integer
+ *          autocorrelation values (the fp32 transform pair only screens candidates).
+ *   d_rmax [stream][n_blocks] double, nullable: r[arg] (exact; `dMax` of :109).
+ */
+int jdsp_pitch_i16_dev(jdsp_ctx *ctx, jdsp_pitch_state *st, const int16_t *d_in, long in_pitch, long n_blocks, int32_t *d_arg,
+                       double *d_rmax);
+/* Host form: n_streams signals of n_samples each (PCM after the program's 44-byte header, :56); stale-tail rule on a
+ * short final block (:60-64); arg / rmax rows hold ceil(n/block) entries, returned in *n_blocks (nullable). */
+int jdsp_pitch_i16(jdsp_ctx *ctx, const jdsp_pitch_params *p, const int16_t *in, long in_pitch, long n_streams, long n_samples,
+                   int32_t *arg, double *rmax, long *n_blocks);
 
 /* ---- C1: FFT overlap-save convolution (AnalySisFreqDomain, Fast_Convolution_Based_3DAudio_Impl.cpp:102-177) */
 typedef struct {

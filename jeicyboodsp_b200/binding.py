@@ -44,6 +44,11 @@ class MfccParams(C.Structure):
                 ("win_a0", C.c_double), ("win_a1", C.c_double), ("pi_literal", C.c_double)]
 
 
+class PitchParams(C.Structure):
+    _fields_ = [("n_fft", C.c_int32), ("block", C.c_int32), ("min_lag", C.c_int32), ("reserved", C.c_int32),
+                ("fs", C.c_double)]
+
+
 def _ptr(x):
     """Raw address of a numpy array / torch tensor / int / None."""
     if x is None:
@@ -70,6 +75,8 @@ ABI_SYMBOLS = [
     "jdsp_fastconv_state_destroy", "jdsp_fastconv_i16_dev", "jdsp_fastconv_mix_i16_dev", "jdsp_fastconv_i16",
     "jdsp_mfcc_params_preset", "jdsp_mfcc_plan_create", "jdsp_mfcc_plan_destroy", "jdsp_mfcc_plan_tables",
     "jdsp_mfcc_frames_i16_dev", "jdsp_mfcc_program_i16",
+    "jdsp_pitch_params_preset", "jdsp_pitch_state_create", "jdsp_pitch_state_reset", "jdsp_pitch_state_destroy",
+    "jdsp_pitch_i16_dev", "jdsp_pitch_i16",
 ]
 
 
@@ -111,6 +118,11 @@ class Library:
     def mfcc_params(self, preset: str) -> MfccParams:
         p = MfccParams()
         self.check(self.lib.jdsp_mfcc_params_preset(preset.encode(), C.byref(p)))
+        return p
+
+    def pitch_params(self, preset: str = "ref") -> PitchParams:
+        p = PitchParams()
+        self.check(self.lib.jdsp_pitch_params_preset(preset.encode(), C.byref(p)))
         return p
 
 
@@ -206,6 +218,23 @@ class Context:
                                                C.c_long(out_pitch), C.byref(got)))
         return got.value
 
+    # ---- pitch (PitchEstimation_method1) ---------------------------------------------------------------------
+    def pitch_state(self, params: PitchParams, n_streams: int) -> "PitchState":
+        return PitchState(self, params, n_streams)
+
+    def pitch(self, x: np.ndarray, params: PitchParams):
+        """Host form: int16 [n_streams, n_samples] -> (arg int32 [n_streams, nb], rmax float64 [n_streams, nb])."""
+        x = np.ascontiguousarray(np.atleast_2d(x), np.int16)
+        S, n = x.shape
+        nb = -(-n // params.block)
+        arg = np.zeros((S, max(nb, 1)), np.int32)
+        rmax = np.zeros((S, max(nb, 1)), np.float64)
+        got = C.c_long(0)
+        self.L.check(self.lib.jdsp_pitch_i16(self.h, C.byref(params), _ptr(x), C.c_long(x.shape[1]), C.c_long(S), C.c_long(n),
+                                             _ptr(arg), _ptr(rmax), C.byref(got)))
+        assert got.value == nb
+        return arg[:, :nb], rmax[:, :nb]
+
     # ---- fast convolution ---------------------------------------------------------------------------------
     def fastconv_state(self, params: FastconvParams, n_sources: int, taps: np.ndarray) -> "FastconvState":
         return FastconvState(self, params, n_sources, taps)
@@ -238,6 +267,26 @@ class Context:
                                                     C.byref(got)))
         assert got.value == rows.shape[0]
         return rows
+
+
+class PitchState:
+    def __init__(self, ctx: Context, params: PitchParams, n_streams: int):
+        self.ctx, self.params, self.n_streams = ctx, params, n_streams
+        self.h = C.c_void_p(0)
+        ctx.L.check(ctx.lib.jdsp_pitch_state_create(ctx.h, C.byref(params), C.c_long(n_streams), C.byref(self.h)))
+
+    def reset(self) -> None:
+        self.ctx.L.check(self.ctx.lib.jdsp_pitch_state_reset(self.ctx.h, self.h))
+
+    def close(self) -> None:
+        if self.h:
+            self.ctx.lib.jdsp_pitch_state_destroy(self.ctx.h, self.h)
+            self.h = C.c_void_p(0)
+
+    def run(self, d_in, in_pitch: int, n_blocks: int, d_arg, d_rmax=None) -> None:
+        """Device form: d_in int16 [n_streams, in_pitch]; d_arg int32 [n_streams, n_blocks]; d_rmax float64 or None."""
+        self.ctx.L.check(self.ctx.lib.jdsp_pitch_i16_dev(self.ctx.h, self.h, _ptr(d_in), C.c_long(in_pitch), C.c_long(n_blocks),
+                                                         _ptr(d_arg), _ptr(d_rmax)))
 
 
 class DenoiseState:

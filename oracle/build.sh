@@ -110,6 +110,11 @@ seds "$MF" "s/^#define MFCC_LEN 12/#define MFCC_LEN 13/" \
     $CXX $OPT $W -I"$SHIM" -Dmain=ref_main -x c++ -c - -o "$TMP/mfcc_mid.o"
 $CXX "$TMP/mfcc_mid.o" "$TMP/run_main.o" -o "$OUT/mfcc_mid" -lm
 
+# ---- PitchEstimation_method1: results are the per-block printf lines on stdout -------------
+PT="$REF/PitchEstimation_method1.cpp"
+$CXX $OPT $W -I"$SHIM" -Dmain=ref_main -c "$PT" -o "$TMP/pitch_ref.o"
+$CXX "$TMP/pitch_ref.o" "$TMP/run_main.o" -o "$OUT/pitch_ref" -lm
+
 cat > "$OUT/README.txt" <<EOF
 Built by oracle/build.sh from the unmodified sources in $REF (g++ $($CXX -dumpversion), $OPT).
 FFT behind the FFTW call sites: oracle/fftw_shim/fftw3.h (radix-2, double, exact pi) - NOT FFTW.

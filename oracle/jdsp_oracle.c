@@ -525,4 +525,74 @@ JO_API long jo_mfcc_program(const jo_mfcc_params *p, const int16_t *x, long n, d
 
 /* M4/M5 tables in dense form for consumers that want them: dct[i][k] (n_cep x n_mel) with the
  * lifter folded in is NOT provided on purpose -- the order of operations above is the contract. */
-JO_API int jo_abi_version(void) { return 1; }
+/* ================================================================================================
+ * Pitch: PitchEstimation_method1.cpp.  Per block: frame = [keep | block] (no window,
+ * :79-84), FFT, |X|^2 (:90-93), unnormalised IFFT / N = circular autocorrelation r[i], i < block (:95-97),
+ * then scan i = block-1 down to min_lag+1 with `>=` (:100-108): the SMALLEST index in (min_lag, block-1]
+ * that attains the maximum.  keep <- block (:112).  The program skips a 44-byte header (:56) and keeps
+ * stale samples in a short final block (:60-64); x is the PCM after the header.
+ * Returns the number of blocks.  arg[b] = iArg, rmax[b] = dMax (the printf of :109).
+ * ---------------------------------------------------------------------------------------------- */
+JO_API long jo_pitch_i16(const int16_t *x, long n, int blk, int nfft, int min_lag, int32_t *arg, double *rmax) {
+    const int keep = nfft - blk;
+    int16_t *buf = (int16_t *)calloc((size_t)blk, sizeof(int16_t));
+    int16_t *kb = (int16_t *)calloc((size_t)keep, sizeof(int16_t));
+    double *a = (double *)calloc(2 * (size_t)nfft, sizeof(double));
+    double *b = (double *)calloc(2 * (size_t)nfft, sizeof(double));
+    long pos = 0, nb = 0;
+    while (jo_read_block(x, n, pos, buf, blk) > 0) {
+        pos += blk;
+        memset(a, 0, sizeof(double) * 2 * (size_t)nfft);
+        for (int i = 0; i < keep; ++i) a[2 * i] = kb[i];                 /* :79-81 */
+        for (int i = 0; i < blk; ++i) a[2 * (keep + i)] = buf[i];        /* :82-84 */
+        jo_dft_exact(a, b, nfft, -1);                                    /* :88 */
+        for (int i = 0; i < nfft; ++i) {                                 /* :90-93 */
+            a[2 * i] = b[2 * i] * b[2 * i] + b[2 * i + 1] * b[2 * i + 1];
+            a[2 * i + 1] = 0.0;
+        }
+        jo_dft_exact(a, b, nfft, +1);                                    /* :94 */
+        double mx = b[2 * (blk - 1)] * 1. / nfft;                        /* :95-99 */
+        int ia = 0;
+        for (int i = blk - 1; i > min_lag; --i) {                        /* :101-108 */
+            const double r = b[2 * i] * 1. / nfft;
+            if (r >= mx) { ia = i; mx = r; }
+        }
+        arg[nb] = ia;
+        rmax[nb] = mx;
+        memcpy(kb, buf + (blk - keep), sizeof(int16_t) * (size_t)keep);  /* :112 */
+        ++nb;
+    }
+    free(buf); free(kb); free(a); free(b);
+    return nb;
+}
+
+/* The same scan on the EXACT circular autocorrelation (sums of integer products, no transform): what the
+ * reference computes up to the rounding noise of its double FFT (~1e-4 absolute on values up to 1e12).
+ * Frames whose two best lags differ by less than that noise are decided by FFT rounding in the reference;
+ * this form decides them by the scan rule on exact values.  rmax is the exact integer sum (the unnormalised
+ * inverse transform of |X|^2 is nfft * sum, so the reference's division by nfft leaves the plain sum). */
+JO_API long jo_pitch_exact_i16(const int16_t *x, long n, int blk, int nfft, int min_lag, int32_t *arg, double *rmax) {
+    const int keep = nfft - blk;
+    int16_t *buf = (int16_t *)calloc((size_t)blk, sizeof(int16_t));
+    int16_t *fr = (int16_t *)calloc((size_t)nfft, sizeof(int16_t));
+    long pos = 0, nb = 0;
+    while (jo_read_block(x, n, pos, buf, blk) > 0) {
+        pos += blk;
+        memcpy(fr + keep, buf, sizeof(int16_t) * (size_t)blk);
+        long long mx = 0;
+        int ia = 0;
+        for (int i = blk - 1; i > min_lag; --i) {
+            long long r = 0;
+            for (int k = 0; k < nfft; ++k) r += (long long)fr[k] * (long long)fr[(k + i) & (nfft - 1)];
+            if (i == blk - 1 || r >= mx) { ia = i; mx = r; }
+        }
+        arg[nb] = ia;
+        rmax[nb] = (double)mx;
+        memcpy(fr, buf + (blk - keep), sizeof(int16_t) * (size_t)keep);
+        ++nb;
+    }
+    free(buf); free(fr);
+    return nb;
+}
+
+JO_API int jo_abi_version(void) { return 2; }

@@ -92,6 +92,8 @@ class Oracle:
         L.jo_fastconv_i16.restype = C.c_long
         L.jo_mfcc_frames.restype = C.c_long
         L.jo_mfcc_program.restype = C.c_long
+        L.jo_pitch_i16.restype = C.c_long
+        L.jo_pitch_exact_i16.restype = C.c_long
 
     # ---- FFT ------------------------------------------------------------------------------------
     def bitrev_table(self, n: int) -> np.ndarray:
@@ -182,6 +184,19 @@ class Oracle:
         assert got == nf, (got, nf)
         return feat
 
+    # ---- pitch -------------------------------------------------------------------
+    def pitch(self, x: np.ndarray, blk: int = 512, nfft: int = 1024, min_lag: int = 100, exact: bool = False):
+        """(arg, rmax) per block; exact=False follows the reference's double-FFT arithmetic, exact=True scans the
+        exact integer autocorrelation (the GPU path's contract)."""
+        x = np.ascontiguousarray(x, np.int16)
+        nb = -(-len(x) // blk)
+        arg, mx = np.zeros(nb, np.int32), np.zeros(nb, np.float64)
+        fn = self.lib.jo_pitch_exact_i16 if exact else self.lib.jo_pitch_i16
+        got = fn(_p(x, C.c_int16), C.c_long(len(x)), C.c_int(blk), C.c_int(nfft), C.c_int(min_lag),
+                 _p(arg, C.c_int32), _p(mx, C.c_double))
+        assert got == nb, (got, nb)
+        return arg, mx
+
     def mfcc_program(self, x: np.ndarray, params: MfccParams) -> np.ndarray:
         x = np.ascontiguousarray(x, np.int16)
         nb = -(-len(x) // (2 * params.hop))
@@ -255,6 +270,21 @@ class RefPrograms:
                 f.write(f"{fi} {fo}")   # NO trailing newline (feof loop would run again)
             self._run(f"mfcc_{preset}", [fl])
             return np.fromfile(fo, np.float64).reshape(-1, n_cep)
+
+    def pitch(self, x: np.ndarray):
+        """PitchEstimation_method1: parse 'Estimation arg %d , dMin %f pitch %f' (:109), one line per block."""
+        with tempfile.TemporaryDirectory() as d:
+            fi = os.path.join(d, "in.wav")
+            with open(fi, "wb") as f:
+                f.write(self.WAV_HEADER + np.ascontiguousarray(x, np.int16).tobytes())
+            log = self._run("pitch_ref", [fi], capture=True)
+        arg, mx = [], []
+        for line in log.splitlines():
+            if line.startswith("Estimation arg"):
+                parts = line.replace(",", " ").split()
+                arg.append(int(parts[2]))
+                mx.append(float(parts[4]))
+        return np.array(arg, np.int32), np.array(mx, np.float64)
 
     def fftprocess(self, x: np.ndarray, forward: bool) -> np.ndarray:
         """The reference's own FFTProcess built with BLOCK_LEN == len(x) (valid for 2^8..2^15)."""

@@ -63,7 +63,7 @@ class GpuBackend:
     def zeros(self, shape, dtype):
         t = self.torch
         m = {np.int16: t.int16, np.float32: t.float32, np.uint8: t.uint8, np.complex64: t.complex64,
-             np.complex128: t.complex128, np.int32: t.int32}
+             np.complex128: t.complex128, np.int32: t.int32, np.float64: t.float64}
         return t.zeros(shape, dtype=m[np.dtype(dtype).type], device="cuda")
 
     def to_dev(self, a: np.ndarray):

@@ -147,6 +147,7 @@ static inline float2 __fmul2_rn(float2 a, float2 b) { return {a.x * b.x, a.y * b
 static inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return {fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline int __clz(unsigned x) { return x ? __builtin_clz(x) : 32; }
 static inline unsigned __brev(unsigned x) {
     unsigned r = 0;
     for (int i = 0; i < 32; ++i) { r = (r << 1) | (x & 1u); x >>= 1; }

@@ -69,6 +69,13 @@ def main() -> None:
     m["ref"] = r.mfcc(xu, "ref", 12)
     m["mid"] = r.mfcc(xu, "mid", 13)
     np.savez_compressed(os.path.join(OUT, "mfcc.npz"), **m)
+    # --- pitch (PitchEstimation_method1) --------------------------------------------
+    pt = {}
+    for stream in (3, 17):
+        xs = synth.denoise_stream(stream, 40_000 + 211)   # gated harmonic "speech": voiced and noise-only blocks, stale tail
+        pt[f"pcm_{stream}"] = xs
+        pt[f"arg_{stream}"], pt[f"rmax_{stream}"] = r.pitch(xs)
+    np.savez_compressed(os.path.join(OUT, "pitch.npz"), **pt)
     for fn in sorted(os.listdir(OUT)):
         if fn.endswith(".npz"):
             print(fn, os.path.getsize(os.path.join(OUT, fn)), "bytes")

@@ -50,3 +50,12 @@ def test_mfcc_golden(oracle):
         got = oracle.mfcc_program(g["pcm"], MfccParams.preset(preset))
         assert got.shape == g[preset].shape
         assert np.abs(got - g[preset]).max() < 1e-9
+
+
+def test_pitch_golden(oracle):
+    g = np.load(os.path.join(G, "pitch.npz"))
+    for stream in (3, 17):
+        for exact in (False, True):
+            arg, mx = oracle.pitch(g[f"pcm_{stream}"], exact=exact)
+            assert np.array_equal(arg, g[f"arg_{stream}"])
+            assert np.allclose(mx, g[f"rmax_{stream}"], rtol=0, atol=1e-6 + 1e-9 * np.abs(mx).max())

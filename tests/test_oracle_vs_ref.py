@@ -70,3 +70,18 @@ def test_mfcc_programs(oracle, refprog, preset, ncep):
     ref = refprog.mfcc(x, preset, ncep)
     assert got.shape == ref.shape
     assert np.abs(got - ref).max() < 1e-9
+
+
+def test_pitch_program(oracle, refprog):
+    """PitchEstimation_method1: arg bit-exact, dMax to the program's printf precision; the exact-integer
+    scan (the GPU path's contract) agrees wherever the two best lags are further apart than the double FFT's rounding noise."""
+    for x in (synth.denoise_stream(5, 50_000 + 123), synth.roundtrip_signal(20_000 + 5),
+              np.random.default_rng(9).normal(0, 4000, 30_000).astype(np.int16), np.zeros(2_000, np.int16)):
+        arg, mx = refprog.pitch(x)
+        oa, om = oracle.pitch(x)
+        assert len(arg) == -(-len(x) // 512)
+        assert np.array_equal(arg, oa)
+        assert np.allclose(mx, om, rtol=0, atol=1e-6 + 1e-15 * np.abs(om).max())
+        ea, em = oracle.pitch(x, exact=True)
+        assert np.array_equal(ea, oa)
+        assert np.abs(em - om).max() <= 1e-9 * max(1.0, np.abs(em).max())

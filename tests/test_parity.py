@@ -301,6 +301,51 @@ def test_mfcc_bench_framing(be, oracle):
     plan.close()
 
 
+# ---- pitch (PitchEstimation_method1) ---------------------------------------------------------
+def test_pitch_reference_fixtures(be):
+    g = np.load(os.path.join(G, "pitch.npz"))
+    x = np.stack([g["pcm_3"], g["pcm_17"]])
+    arg, rmax = be.ctx.pitch(x, be.L.pitch_params("ref"))
+    for i, stream in enumerate((3, 17)):
+        assert np.array_equal(arg[i], g[f"arg_{stream}"])          # integer fact: bit-exact
+        # exact integers here; the program prints a double-FFT result (rounding noise ~1e-15 of values up to 1e12) with %f
+        assert np.allclose(rmax[i], g[f"rmax_{stream}"], rtol=1e-12, atol=1e-5)
+
+
+def test_pitch_dev_chunked_and_edge_inputs(be, oracle):
+    """Device form fed in chunks equals one shot and the exact-integer oracle; noise, silence, a DC step and full-scale
+    square waves (ties, zero frames, largest magnitudes) all decide by the reference's scan rule on exact values."""
+    rng = np.random.default_rng(21)
+    n_blocks, H = 9, 512
+    sigs = [synth.denoise_stream(7, n_blocks * H), rng.normal(0, 3000, n_blocks * H), np.zeros(n_blocks * H),
+            np.full(n_blocks * H, 1000.0), 32767.0 * np.sign(np.sin(2 * np.pi * np.arange(n_blocks * H) / 128.0) + 1e-9),
+            rng.integers(-32768, 32768, n_blocks * H).astype(np.float64)]
+    x = np.stack([np.clip(np.round(s), -32768, 32767).astype(np.int16) for s in sigs])
+    S = x.shape[0]
+    p = be.L.pitch_params("ref")
+    d_in = be.to_dev(x)
+    one = be.zeros((S, n_blocks), np.int32)
+    one_r = be.zeros((S, n_blocks), np.float64)
+    st = be.ctx.pitch_state(p, S)
+    st.run(d_in, n_blocks * H, n_blocks, one, one_r)
+    be.sync()
+    one, one_r = be.to_host(one).copy(), be.to_host(one_r).copy()
+    for s in range(S):
+        ea, em = oracle.pitch(x[s], exact=True)
+        assert np.array_equal(one[s], ea), (s, one[s], ea)
+        assert np.array_equal(one_r[s], em)                         # exact integers in float64
+    st.reset()
+    parts = []
+    for b0, nb in ((0, 1), (1, 5), (6, 3)):
+        chunk = be.to_dev(x[:, b0 * H:(b0 + nb) * H])
+        out = be.zeros((S, nb), np.int32)
+        st.run(chunk, nb * H, nb, out, None)
+        be.sync()
+        parts.append(be.to_host(out).copy())
+    assert np.array_equal(np.concatenate(parts, axis=1), one)
+    st.close()
+
+
 def test_emulator_fiber_order_invariance():
     """Missing-barrier detector for the emulated build: ascending and descending fiber schedules must agree."""
     from backends import EmulBackend
