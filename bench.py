@@ -317,9 +317,9 @@ def main_gpu(args):
                        "l2": f"inputs {S * n * 2 / 1e9:.2f} GB per pass >> 126 MB L2 (no flush needed)",
                        "frames_per_s": value * 1e6 / HOP},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                         "traffic": traffic, "traffic_source": "ncu --set full capture of this launch, profiles/round1/ncu_bench_kernel_summary.txt", "peak_source": peak_src, "kernel": "jdsp::denoise_kernel<256,8,MODE>",
+                         "traffic": traffic, "traffic_source": "ncu --set full capture of this launch, profiles/round1/ncu_bench_kernel_summary.txt", "peak_source": peak_src, "kernel": "jdsp::denoise_stream_kernel<256,MODE,16>",
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_kernel_ms, "per_mode_ms": per_mode,
-                         "note": "4 B/sample (int16 in + int16 out); the kernel is fp32-issue/shared-memory bound, see DESIGN.md"},
+                         "note": "4 B/sample (int16 in + int16 out); one half warp per stream, bound by per-warp issue latency (fp32 FFT arithmetic + shared-memory exchanges at 3.5 warps per scheduler), see DESIGN.md"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "parity": parity,
         }
         sys.stdout.flush()

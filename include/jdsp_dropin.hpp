@@ -126,5 +126,45 @@ class FastConvStream {
     int16_t *d_in_ = nullptr, *d_out_ = nullptr;
 };
 
+// void CalcPitch(short *psInputBuffer, int iFrameCount)  (PitchEstimation_method1.cpp:30,69-116): one stream, one block per
+// call; the keep buffer (static rgssKeepBuffer, :73) lives in the state.  Returns what the reference prints (:109).
+class PitchStream {
+  public:
+    struct Result { int iArg; double dMax; double dPitch; };
+    explicit PitchStream(const char *preset = "ref") {
+        check(jdsp_pitch_params_preset(preset, &p_), "pitch preset");
+        check(jdsp_pitch_state_create(default_ctx(), &p_, 1, &st_), "pitch state");
+        check(jdsp_malloc(default_ctx(), (void **)&d_in_, p_.block * sizeof(int16_t)), "malloc");
+        check(jdsp_malloc(default_ctx(), (void **)&d_arg_, sizeof(int32_t)), "malloc");
+        check(jdsp_malloc(default_ctx(), (void **)&d_max_, sizeof(double)), "malloc");
+    }
+    ~PitchStream() {
+        jdsp_pitch_state_destroy(default_ctx(), st_);
+        jdsp_free(default_ctx(), d_in_);
+        jdsp_free(default_ctx(), d_arg_);
+        jdsp_free(default_ctx(), d_max_);
+    }
+    Result CalcPitch(const short *psInputBuffer, int iFrameCount) {
+        if (iFrameCount != p_.block) throw std::invalid_argument("iFrameCount must equal BLOCK_SIZE");
+        jdsp_ctx *c = default_ctx();
+        int32_t arg = 0;
+        double mx = 0;
+        check(jdsp_memcpy_h2d(c, d_in_, psInputBuffer, p_.block * sizeof(int16_t)), "h2d");
+        check(jdsp_pitch_i16_dev(c, st_, d_in_, p_.block, 1, d_arg_, d_max_), "pitch");
+        check(jdsp_memcpy_d2h(c, &arg, d_arg_, sizeof(arg)), "d2h");
+        check(jdsp_memcpy_d2h(c, &mx, d_max_, sizeof(mx)), "d2h");
+        check(jdsp_sync(c), "sync");
+        return Result{arg, mx, p_.fs / (double)arg};   // DEFAULT_SAMPLINGRATE / (double)iArg (:109)
+    }
+    const jdsp_pitch_params &params() const { return p_; }
+
+  private:
+    jdsp_pitch_params p_;
+    jdsp_pitch_state *st_ = nullptr;
+    int16_t *d_in_ = nullptr;
+    int32_t *d_arg_ = nullptr;
+    double *d_max_ = nullptr;
+};
+
 }  // namespace jdsp
 #endif

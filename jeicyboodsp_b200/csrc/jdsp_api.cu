@@ -160,7 +160,8 @@ static int launch_c2c_fused(jdsp_ctx *c, const cx<float> *in, cx<float> *out, lo
     const long grid_cap = 1;                            // the emulator runs CTAs one after another
 #endif
     // look-ahead: enough transforms in flight that a row item is rarely grabbed before its columns are done
-    long look = (2 * grid_cap + Geo::TA + Geo::TB - 1) / (Geo::TA + Geo::TB) + 2;
+    long look = (2 * grid_cap + Geo::TA + Geo::TB - 1) / (Geo::TA + Geo::TB) + 2;   // shorter look-aheads were measured slower (rows stall on columns)
+    if (const char *e = getenv("JDSP_FFT_FUSED_LOOK")) look = atol(e) > 0 ? atol(e) : look;
     if (look > batch) look = batch;
     const long ring = 2 * look;
     TRY(ensure_scratch(c, (size_t)ring * N * sizeof(cx<float>) + (2 * (size_t)batch + 8) * sizeof(unsigned)));

@@ -186,40 +186,69 @@ static int launch_denoise_stream(jdsp_ctx *c, const DenoiseArgs &a, int mode) {
     }
     return launch_check(c);
 }
-static bool denoise_use_tile_kernel() {
-    const char *e = getenv("JDSP_DENOISE_KERNEL");
-    return e && !strcmp(e, "tile");
+// streams one wave of the stream-group kernel can hold on this device (8 CTAs per SM at 128 registers per thread)
+template <int NC> static long denoise_stream_wave(jdsp_ctx *c) {
+    using Geo = StreamGeom<NC>;
+    int per_sm = 8;
+#ifndef JDSP_EMUL
+    auto kfn = denoise_stream_kernel<NC, 0, 16>;
+    if (opt_in_smem(kfn, Geo::SMEM) != JDSP_OK ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, Geo::NT, Geo::SMEM) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+#endif
+    return (long)per_sm * Geo::GPC * c->sm_count;
 }
 
-// stream0/n: the slice of the state's streams this launch covers
+// stream0/n: the slice of the state's streams this launch covers.
+// Two kernels share the state layout.  The stream-group kernel (one half warp / warp per stream) is the faster one when the
+// device is full of streams; it walks a stream sequentially, so all its CTAs run equally long and a partly filled last wave
+// costs a whole pass.  The CTA-per-stream kernel works on 8 (4) frames of a stream at a time and degrades gracefully.  Rule
+// (measured, 512-pt preset on 148 SMs: 148 / 592 / 1184 / 2368 / 4096 streams -> tile 3.8x / 2.3x / 1.2x / 0.94x / 0.94x the
+// stream kernel's time): whole waves, and a remainder of at least 7/16 of a wave, go to the stream-group kernel; a smaller
+// remainder goes to the CTA-per-stream kernel.  JDSP_DENOISE_KERNEL=tile|stream forces one.
 static int denoise_launch_slice(jdsp_ctx *c, jdsp_denoise_state *st, cudaStream_t stream, long stream0, long n, const int16_t *d_in,
                                 long in_pitch, long n_blocks, int16_t *d_out, long out_pitch, float *d_out_f32, long f32_pitch,
                                 uint8_t *d_vad) {
     const jdsp_denoise_params &p = st->p;
     const long NC = p.n_fft / 2, H = p.hop;
-    void *tw, *twr;
+    void *tw, *twr, *tw8 = nullptr;
     TRY(get_table(c, 0, (int)NC, &tw));
     TRY(get_table(c, 2, (int)NC, &twr));
-    DenoiseArgs a;
-    a.in = d_in; a.in_pitch = in_pitch; a.n_blocks = n_blocks;
-    a.out = d_out; a.out_pitch = out_pitch; a.out_f32 = d_out_f32; a.f32_pitch = f32_pitch; a.vad = d_vad;
-    a.win_half = st->d_win_half; a.win_vad = st->d_win_vad; a.tw = (const cf *)tw; a.twr = (const float2 *)twr;
-    a.st_seen = st->d_seen + stream0; a.st_run = st->d_run + stream0; a.st_pub = st->d_pub + stream0;
-    a.st_avg = st->d_avg + stream0 * (NC + 1); a.st_ns = st->d_ns + stream0 * (NC + 1);
-    a.st_prev = st->d_prev + stream0 * H; a.st_ola = st->d_ola + stream0 * H;
-    a.n_streams = n; a.zcr_thr = p.zcr_thr; a.noise_frames = p.noise_frames; a.energy_thr = p.energy_thr;
-    a.skip_blocks = st->seen < 2 ? 2 - st->seen : 0;
+    const char *force = getenv("JDSP_DENOISE_KERNEL");
+    const bool e8 = p.n_fft == 512 && getenv("JDSP_STREAM_E8");   // experiment: a warp per stream, 8 points per thread
+    if (e8) TRY(get_table(c, 5, (int)NC, &tw8));
+    const long wave = p.n_fft == 512 ? denoise_stream_wave<256>(c) : denoise_stream_wave<512>(c);
+    long n_tile = n % wave, n_main = n - n_tile;
+    if (n_tile * 16 >= wave * 7) { n_main = n; n_tile = 0; }
+    if (force && !strcmp(force, "tile")) { n_main = 0; n_tile = n; }
+    if ((force && !strcmp(force, "stream")) || e8) { n_main = n; n_tile = 0; }
+    auto slice = [&](long s0, long cnt) {
+        DenoiseArgs a;
+        const long g0 = stream0 + s0;   // index into the state arrays
+        a.in = d_in + s0 * in_pitch; a.in_pitch = in_pitch; a.n_blocks = n_blocks;
+        a.out = d_out ? d_out + s0 * out_pitch : nullptr; a.out_pitch = out_pitch;
+        a.out_f32 = d_out_f32 ? d_out_f32 + s0 * f32_pitch : nullptr; a.f32_pitch = f32_pitch;
+        a.vad = d_vad ? d_vad + s0 * n_blocks : nullptr;
+        a.win_half = st->d_win_half; a.win_vad = st->d_win_vad; a.tw = (const cf *)tw; a.twr = (const float2 *)twr;
+        a.st_seen = st->d_seen + g0; a.st_run = st->d_run + g0; a.st_pub = st->d_pub + g0;
+        a.st_avg = st->d_avg + g0 * (NC + 1); a.st_ns = st->d_ns + g0 * (NC + 1);
+        a.st_prev = st->d_prev + g0 * H; a.st_ola = st->d_ola + g0 * H;
+        a.n_streams = cnt; a.zcr_thr = p.zcr_thr; a.noise_frames = p.noise_frames; a.energy_thr = p.energy_thr;
+        a.skip_blocks = st->seen < 2 ? 2 - st->seen : 0;
+        return a;
+    };
     cudaStream_t saved = c->stream;
     c->stream = stream;
-    int rc;
-    if (denoise_use_tile_kernel()) rc = (p.n_fft == 512) ? launch_denoise<256, 8>(c, a, p.mode) : launch_denoise<512, 4>(c, a, p.mode);
-    else if (p.n_fft == 512 && getenv("JDSP_STREAM_E8")) {   // experiment: a warp per stream, 8 points per thread
-        void *tw8;
-        TRY(get_table(c, 5, (int)NC, &tw8));
-        a.tw = (const cf *)tw8;
-        rc = launch_denoise_stream<256, 8>(c, a, p.mode);
+    int rc = JDSP_OK;
+    if (n_main > 0) {
+        DenoiseArgs a = slice(0, n_main);
+        if (e8) { a.tw = (const cf *)tw8; rc = launch_denoise_stream<256, 8>(c, a, p.mode); }
+        else rc = (p.n_fft == 512) ? launch_denoise_stream<256>(c, a, p.mode) : launch_denoise_stream<512>(c, a, p.mode);
     }
-    else rc = (p.n_fft == 512) ? launch_denoise_stream<256>(c, a, p.mode) : launch_denoise_stream<512>(c, a, p.mode);
+    if (rc == JDSP_OK && n_tile > 0) {
+        const DenoiseArgs a = slice(n_main, n_tile);
+        rc = (p.n_fft == 512) ? launch_denoise<256, 8>(c, a, p.mode) : launch_denoise<512, 4>(c, a, p.mode);
+    }
     c->stream = saved;
     return rc;
 }

@@ -285,6 +285,37 @@ template <typename T> JDSP_DEV cx<T> ld_cg(const cx<T> *p) {   // scratch writte
     else { const double2 v = __ldcg(reinterpret_cast<const double2 *>(p)); return cmake<T>(v.x, v.y); }
 #endif
 }
+// L2 eviction-priority policies (createpolicy) and hinted 8-byte accesses: the scratch ring should stay in L2 between the
+// column and the row pass (evict_last), the input and output stream through once (evict_first).
+JDSP_DEV uint64_t l2_policy(bool keep) {
+#ifdef JDSP_EMUL
+    return keep ? 1u : 0u;
+#else
+    uint64_t pol;
+    if (keep) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+#endif
+}
+JDSP_DEV cx<float> ld_hint(const cx<float> *p, uint64_t pol) {
+#ifdef JDSP_EMUL
+    (void)pol; return *p;
+#else
+    cx<float> v;
+    asm volatile("ld.global.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol) : "memory");
+    return v;
+#endif
+}
+JDSP_DEV void st_hint(cx<float> *p, cx<float> v, uint64_t pol) {
+#ifdef JDSP_EMUL
+    (void)pol; *p = v;
+#else
+    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+#endif
+}
+template <typename T> JDSP_DEV cx<T> ld_hint(const cx<T> *p, uint64_t) { return *p; }
+template <typename T> JDSP_DEV void st_hint(cx<T> *p, cx<T> v, uint64_t) { *p = v; }
+
 template <typename T, int N1, int N2, bool INV>
 struct FusedGeom {
     static constexpr int THREADS = 512;
@@ -311,6 +342,7 @@ fft_fourstep_fused_kernel(const cx<T> *__restrict__ in, cx<T> *tmp, cx<T> *__res
     unsigned *item_sh = reinterpret_cast<unsigned *>(smem_raw);
     // item numbering: steps 0..look-1 hold TA column items; steps look..batch-1 hold TA column + TB row items;
     // steps batch..batch+look-1 hold TB row items (rows of transform step-look)
+    const uint64_t pol_stream = l2_policy(false), pol_keep = l2_policy(true);
     const long lk = look < batch ? look : batch;
     const long n_head = lk * TA, n_mid = (batch - lk) * (TA + TB), n_items = n_head + n_mid + lk * TB;
     for (;;) {
@@ -338,7 +370,7 @@ fft_fourstep_fused_kernel(const cx<T> *__restrict__ in, cx<T> *tmp, cx<T> *__res
             const cx<T> *src = in + f * N + c0 + sc;
             cx<T> st[E];
 #pragma unroll
-            for (int i = 0; i < E; ++i) st[i] = src[(long)(sr + (THREADS / CT) * i) * N2];
+            for (int i = 0; i < E; ++i) st[i] = ld_hint(src + (long)(sr + (THREADS / CT) * i) * N2, pol_stream);
             const long col = c0 + c;
             const cx<T> wa = twN[col * t], b1 = twN[col * G1], b4 = twN[col * (4 * G1)];
 #pragma unroll
@@ -371,7 +403,7 @@ fft_fourstep_fused_kernel(const cx<T> *__restrict__ in, cx<T> *tmp, cx<T> *__res
 #pragma unroll
             for (int i = 0; i < E; ++i) {
                 const int k1 = sr + (THREADS / CT) * i;
-                dst[(long)k1 * N2] = sm[sc * P1 + pad16(k1)];
+                st_hint(dst + (long)k1 * N2, sm[sc * P1 + pad16(k1)], pol_keep);
             }
             __threadfence();          // publish the tile before the counter moves
             __syncthreads();
@@ -398,7 +430,7 @@ fft_fourstep_fused_kernel(const cx<T> *__restrict__ in, cx<T> *tmp, cx<T> *__res
                 const int k2 = ok + (THREADS / RT) * i;
                 cx<T> v = sm[orr * P2 + pad16(k2)];
                 v.x *= scale; v.y *= scale;
-                dst[(long)k2 * N1] = v;
+                st_hint(dst + (long)k2 * N1, v, pol_stream);
             }
             __syncthreads();          // all reads of the scratch slot by this tile are complete
             if (threadIdx.x == 0) { __threadfence(); atomicAdd(sy.done_b + f, 1u); }

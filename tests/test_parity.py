@@ -116,9 +116,18 @@ def test_roundtrip_dev_precast(be, oracle, n_fft, n_blocks):
 
 
 # ------------------------------------------------------------------------------------------------ denoise
+@pytest.fixture(params=["stream", "tile"])
+def dkernel(request, monkeypatch):
+    """Both denoise kernels behind the same entry points: 'stream' = one thread group per stream (what a device full of
+    streams runs), 'tile' = one CTA per stream (what a few streams run).  The library picks by stream count; the tests
+    force each (the variable is read at every launch)."""
+    monkeypatch.setenv("JDSP_DENOISE_KERNEL", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("preset", ["bench", "ref"])
 @pytest.mark.parametrize("mode,nm", [(SS, "ss"), (WIENER, "wiener")])
-def test_denoise_reference_fixtures(be, preset, mode, nm):
+def test_denoise_reference_fixtures(be, dkernel, preset, mode, nm):
     g = np.load(os.path.join(G, "denoise.npz"))
     x = np.stack([g["pcm_3"], g["pcm_17"]])
     got = be.ctx.denoise(x, be.L.denoise_params(preset, mode))
@@ -128,7 +137,7 @@ def test_denoise_reference_fixtures(be, preset, mode, nm):
 
 @pytest.mark.parametrize("preset", ["bench", "ref"])
 @pytest.mark.parametrize("mode", [SS, WIENER])
-def test_denoise_dev_state_machine_and_precast(be, oracle, preset, mode):
+def test_denoise_dev_state_machine_and_precast(be, dkernel, oracle, preset, mode):
     p = be.L.denoise_params(preset, mode)
     H = p.hop
     nb = 150 if be.name == "emul" else 400
@@ -164,7 +173,7 @@ def test_denoise_dev_state_machine_and_precast(be, oracle, preset, mode):
 
 
 @pytest.mark.parametrize("preset", ["bench", "ref"])
-def test_denoise_chunked_equals_one_shot(be, preset):
+def test_denoise_chunked_equals_one_shot(be, dkernel, preset):
     """The explicit stream state replaces the reference's statics: feeding a stream in pieces of whole blocks
     (including pieces shorter than the 2-block warm-up) must give bit-identical output."""
     p = be.L.denoise_params(preset, SS)
@@ -186,7 +195,7 @@ def test_denoise_chunked_equals_one_shot(be, preset):
 
 
 @pytest.mark.parametrize("nb", [0, 1, 2, 3])
-def test_denoise_short_inputs(be, oracle, nb):
+def test_denoise_short_inputs(be, dkernel, oracle, nb):
     p = be.L.denoise_params("bench", SS)
     x = synth.denoise_stream(1, max(nb * p.hop, 1))[: nb * p.hop][None, :]
     if nb == 0:
@@ -197,7 +206,7 @@ def test_denoise_short_inputs(be, oracle, nb):
         assert_i16_parity(got[0], oracle.denoise(x[0], ODP.preset("bench", SS)).out, max_flip_frac=5e-3)
 
 
-def test_denoise_identity_property(be):
+def test_denoise_identity_property(be, dkernel):
     """Always-voice input => noise estimate stays 0 => out = delayed input x window overlap sum."""
     p = be.L.denoise_params("bench", WIENER)
     n = 40 * p.hop
@@ -208,6 +217,33 @@ def test_denoise_identity_property(be):
     m = np.arange(len(got))
     expect = x[0][m + p.hop] * (w[p.hop + (m % p.hop)] + w[m % p.hop])
     assert np.abs(got - expect).max() <= 1.0 + 1e-4 * 9000
+
+
+def test_denoise_wave_split_and_state_handover(be, oracle, monkeypatch):
+    """More streams than one wave of the stream-group kernel: whole waves run on it, the small remainder on the CTA-per-
+    stream kernel, both over slices of ONE state.  A second call (forced the other way round) continues every stream
+    from that state, so the two kernels must read and write the carry state identically."""
+    monkeypatch.delenv("JDSP_DENOISE_KERNEL", raising=False)
+    if be.name == "emul":
+        wave = 8 * 4 * 2                       # 8 CTAs x 4 streams x the emulator's 2 SMs
+    else:
+        wave = 8 * 4 * be.torch.cuda.get_device_properties(0).multi_processor_count
+    p = be.L.denoise_params("bench", SS)
+    H, nb1, nb2 = p.hop, 24, 8
+    S = wave + 3
+    base = np.stack([synth.denoise_stream(60 + s, (nb1 + nb2) * H) for s in range(5)])
+    x = base[np.arange(S) % 5]
+    st = be.ctx.denoise_state(p, S)
+    d_out1 = be.zeros((S, (nb1 - 2) * H), np.int16)
+    d_out2 = be.zeros((S, nb2 * H), np.int16)
+    assert st.run(be.to_dev(x[:, : nb1 * H]), nb1 * H, nb1, d_out1, (nb1 - 2) * H) == nb1 - 2
+    monkeypatch.setenv("JDSP_DENOISE_KERNEL", "tile")      # the streams the stream-group kernel started are finished by the other kernel
+    assert st.run(be.to_dev(x[:, nb1 * H:]), nb2 * H, nb2, d_out2, nb2 * H) == nb2
+    got = np.concatenate([be.to_host(d_out1), be.to_host(d_out2)], axis=1)
+    refs = [oracle.denoise(base[i], ODP.preset("bench", SS)).out for i in range(5)]
+    for s in list(range(5)) + [wave - 1, wave, wave + 1, wave + 2]:
+        assert_i16_parity(got[s], refs[s % 5], max_flip_frac=5e-3, what=f"stream {s}")
+    st.close()
 
 
 # --------------------------------------------------------------------------------------------- fast convolution
@@ -346,15 +382,28 @@ def test_pitch_dev_chunked_and_edge_inputs(be, oracle):
     st.close()
 
 
-def test_emulator_fiber_order_invariance():
+@pytest.mark.parametrize("what", ["denoise_tile", "denoise_stream", "denoise_stream_ref", "pitch", "fft4096"])
+def test_emulator_fiber_order_invariance(what, monkeypatch):
     """Missing-barrier detector for the emulated build: ascending and descending fiber schedules must agree."""
     from backends import EmulBackend
     be = _CACHE.setdefault("emul", EmulBackend())
-    p = be.L.denoise_params("bench", SS)
-    x = np.stack([synth.denoise_stream(s, 30 * p.hop) for s in range(2)])
+    if what.startswith("denoise"):
+        monkeypatch.setenv("JDSP_DENOISE_KERNEL", "tile" if what == "denoise_tile" else "stream")
+        p = be.L.denoise_params("ref" if what.endswith("_ref") else "bench", SS)
+        x = np.stack([synth.denoise_stream(s, 30 * p.hop) for s in range(3)])   # 3 streams: a half-filled warp too
+        run = lambda: be.ctx.denoise(x, p).copy()
+    elif what == "pitch":
+        x = np.stack([synth.denoise_stream(s, 9 * 512) for s in range(3)])
+        run = lambda: np.concatenate([a.astype(np.float64) for a in be.ctx.pitch(x, be.L.pitch_params("ref"))], axis=1)
+    else:
+        z = np.random.default_rng(3).uniform(-1, 1, (3, 4096, 2)).astype(np.float32).view(np.complex64)[..., 0]
+        def run():
+            out = np.zeros_like(z)
+            be.ctx.fft_c2c_f32(np.ascontiguousarray(z), out, 4096, 3, True)
+            return out
     res = []
     for order in (+1, -1):
         be.set_order(order)
-        res.append(be.ctx.denoise(x, p).copy())
+        res.append(run())
     be.set_order(+1)
     assert np.array_equal(res[0], res[1])

@@ -21,7 +21,7 @@ def built():
 
 
 def test_programs_build_without_cuda_headers(built):
-    for p in ("jdsp_fft_roundtrip", "jdsp_denoise", "jdsp_fastconv", "jdsp_mfcc", "jdsp_blockwise"):
+    for p in ("jdsp_fft_roundtrip", "jdsp_denoise", "jdsp_fastconv", "jdsp_mfcc", "jdsp_blockwise", "jdsp_pitch"):
         assert os.path.exists(os.path.join(built, p))
 
 
@@ -84,3 +84,27 @@ def test_mfcc_program_writes_the_mfc_format(built, tmp_path):
         _run(built, "jdsp_mfcc", str(fl), preset)
         rows = np.fromfile(fo, np.float64).reshape(-1, ncep)   # raw double[n_cep] rows: what GMMAlgorithm_* read
         assert_float_parity(rows, g[preset], f"mfcc program {preset}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("how", ["batched", "block"])
+def test_pitch_program_prints_the_reference_lines(built, tmp_path, how):
+    """Same stdout lines as PitchEstimation_method1 (:109): arg bit-exact, dMax / pitch as printed."""
+    g = np.load(os.path.join(G, "pitch.npz"))
+    fi = tmp_path / "in.wav"
+    x = g["pcm_3"] if how == "batched" else g["pcm_3"][:6 * 512 + 100]
+    fi.write_bytes(HDR + x.tobytes())
+    args = [os.path.join(built, "jdsp_pitch"), str(fi)] + (["block"] if how == "block" else [])
+    out = subprocess.run(args, check=True, stdin=subprocess.DEVNULL, stdout=subprocess.PIPE).stdout.decode()
+    rows = [ln.replace(",", " ").split() for ln in out.splitlines() if ln.startswith("Estimation arg")]
+    arg = np.array([int(r[2]) for r in rows])
+    mx = np.array([float(r[4]) for r in rows])
+    pitch = np.array([float(r[6]) for r in rows])
+    nb = -(-len(x) // 512)
+    assert len(arg) == nb and out.rstrip().endswith("Processing End")
+    if how == "batched":
+        assert np.array_equal(arg, g["arg_3"])
+        assert np.allclose(mx, g["rmax_3"], rtol=1e-12, atol=1e-5)
+    else:   # a shorter file: whole blocks agree with the fixture, the short last block is checked for the stale-tail rule
+        assert np.array_equal(arg[: nb - 1], g["arg_3"][: nb - 1])
+    assert np.allclose(pitch, 16000.0 / arg, rtol=0, atol=1e-6)

@@ -1,4 +1,4 @@
-"""Measure the other BASELINE.json configs (1, 3, 4, 5) on one GPU: CUDA-event timing, algorithmic bytes vs the
+"""Measure the other BASELINE.json configs (1, 3, 4, 5) and the pitch path on one GPU: CUDA-event timing, algorithmic bytes vs the
 measured HBM peak, and a parity spot check against the oracle for each.  Writes one JSON object per config.
 
     python tools/bench_extras.py [--out gpurun_out/extras.json] [--quick]
@@ -181,6 +181,35 @@ if want("mfcc"):
           "frames_per_s": U * nf / med * 1e3, "algorithmic_bytes": alg, "gbs": alg / med / 1e6, "frac_hbm": alg / med / 1e6 / PEAK,
           "parity_max_rel_peak": worst})
     plan.close()
+
+# ---- pitch by FFT autocorrelation, 1024-pt frames, hop 512 ------------------------------------------
+if want("pitch"):
+    S = 4096 if not args.quick else 512
+    n = 960_000 if not args.quick else 96_000
+    p = L.pitch_params("ref")
+    H = p.block
+    nb = n // H
+    n = nb * H
+    x = synth.denoise_streams_torch(S, n, dev)
+    arg = torch.empty((S, nb), dtype=torch.int32, device=dev)
+    rmax = torch.empty((S, nb), dtype=torch.float64, device=dev)
+    st = ctx.pitch_state(p, S)
+
+    def run_pitch():
+        st.reset()
+        st.run(x, n, nb, arg, rmax)
+    med, best = timed(run_pitch, warm=2, reps=5)
+    alg = S * n * 2 + S * nb * 12
+    torch.cuda.synchronize()
+    same = True
+    for s_ in (0, S // 2, S - 1):
+        ea, em = o.pitch(x[s_].cpu().numpy(), exact=True)
+        same = same and bool(np.array_equal(arg[s_].cpu().numpy(), ea)) and bool(np.array_equal(rmax[s_].cpu().numpy(), em))
+    emit({"config": "pitch", "streams": S, "samples_per_stream": n, "frames": S * nb, "ms": med, "msamples_s": S * n / med / 1e3,
+          "frames_per_s": S * nb / med * 1e3, "algorithmic_bytes": alg, "gbs": alg / med / 1e6, "frac_hbm": alg / med / 1e6 / PEAK,
+          "parity_arg_and_rmax_bit_exact": same})
+    st.close()
+    del x
 
 os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
 with open(args.out, "w") as f:

@@ -9,7 +9,7 @@ timeout 300 python tools/prof_denoise.py > gpurun_out/prof_$TAG.log 2>&1; RC=$?
 tail -4 gpurun_out/prof_$TAG.log
 if [ "$2" = "ncu" ] && [ $RC -eq 0 ]; then
   python tools/prof_denoise.py --iters 2 > /dev/null 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:denoise_kernel -s 2 -c 2 -o gpurun_out/denoise_$TAG python tools/prof_denoise.py --iters 2 > gpurun_out/ncu_$TAG.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:denoise_ -s 2 -c 2 -o gpurun_out/denoise_$TAG python tools/prof_denoise.py --iters 2 > gpurun_out/ncu_$TAG.log 2>&1
   tail -2 gpurun_out/ncu_$TAG.log
 fi
 timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"
