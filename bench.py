@@ -241,8 +241,8 @@ def main_gpu(args):
     avg_kernel_ms = statistics.mean(kern_ms)
     achieved = alg_bytes / (avg_kernel_ms * 1e-3) / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this exact workload, from the committed
-    # `ncu --set full` capture profiles/round1/ncu_bench_kernel_summary.txt (7.882 GB read + 7.837 GB written)
-    traffic = 15_718_634_000 if (S == 4096 and n == 960_000) else None
+    # `ncu --set full` capture profiles/round1/ncu_bench_kernel_summary.txt (7.881 GB read + 7.835 GB written, denoise_stream_kernel<256,0,16>)
+    traffic = 15_715_987_000 if (S == 4096 and n == 960_000) else None
 
     # ---- parity spot check on the very data that was timed (8 streams through the oracle) -------------------
     parity = None

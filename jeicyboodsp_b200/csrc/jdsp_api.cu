@@ -95,6 +95,7 @@ static int launch_c2c_small(jdsp_ctx *c, const cx<T> *in, cx<T> *out, long batch
 template <int N, bool INV>
 static int launch_c2c_pipe(jdsp_ctx *c, const cx<float> *in, cx<float> *out, long batch, const cx<float> *tw) {
     using Geo = FftPipeGeom<N>;
+    if (Geo::E == 32) { void *t32; TRY(get_table(c, 6, N, &t32)); tw = (const cx<float> *)t32; }
     auto kfn = fft_c2c_pipe_kernel<N, INV>;
     TRY(opt_in_smem(kfn, Geo::SMEM));
     int per_sm = 1;
@@ -103,6 +104,23 @@ static int launch_c2c_pipe(jdsp_ctx *c, const cx<float> *in, cx<float> *out, lon
     if (per_sm < 1) return fail(JDSP_ERR_CUDA, "pipelined FFT kernel does not fit an SM");
 #endif
     JDSP_LAUNCH_PTR(kfn, dim3(grid_for(c, batch, per_sm)), dim3(Geo::THREADS), Geo::SMEM, c->stream, in, out, batch, tw, 1.0f);
+    return launch_check(c);
+}
+
+// fp32 N = 8192 / 16384 on chip, 32 points per thread (JDSP_FFT_NO_BIG=1 falls back to the pipelined / four-step kernels)
+template <int N, bool INV>
+static int launch_c2c_big(jdsp_ctx *c, const cx<float> *in, cx<float> *out, long batch) {
+    using Geo = FftBigGeom<N>;
+    void *t32;
+    TRY(get_table(c, 6, N, &t32));
+    auto kfn = fft_c2c_big_kernel<N, INV>;
+    TRY(opt_in_smem(kfn, Geo::SMEM));
+    int per_sm = 1;
+#ifndef JDSP_EMUL
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, Geo::THREADS, Geo::SMEM));
+    if (per_sm < 1) return fail(JDSP_ERR_CUDA, "on-chip FFT kernel does not fit an SM");
+#endif
+    JDSP_LAUNCH_PTR(kfn, dim3(grid_for(c, batch, per_sm)), dim3(Geo::THREADS), Geo::SMEM, c->stream, in, out, batch, (const cx<float> *)t32, 1.0f);
     return launch_check(c);
 }
 
@@ -180,16 +198,20 @@ template <typename T, bool INV>
 static int fft_dispatch(jdsp_ctx *c, const cx<T> *in, cx<T> *out, int n, long batch) {
     const int tkind = sizeof(T) == 4 ? 0 : 1;
     void *tw = nullptr;
-    if (n <= 8192 || (n == 16384 && sizeof(T) == 4 && getenv("JDSP_FFT_ONCHIP16K"))) TRY(get_table(c, tkind, n, &tw));
+    if (n <= 8192) TRY(get_table(c, tkind, n, &tw));
     const cx<T> *t = (const cx<T> *)tw;
     switch (n) {
 #define SMALL(NN) case NN: return launch_c2c_small<T, NN, INV>(c, in, out, batch, t);
+        case 8192:
+            if constexpr (sizeof(T) == 4) { if (!getenv("JDSP_FFT_NO_BIG")) return launch_c2c_big<8192, INV>(c, (const cx<float> *)in, (cx<float> *)out, batch); }
+            if constexpr (sizeof(T) == 4) { if (!getenv("JDSP_FFT_NO_PIPE")) return launch_c2c_pipe<8192, INV>(c, (const cx<float> *)in, (cx<float> *)out, batch, (const cx<float> *)t); }
+            return launch_c2c_small<T, 8192, INV>(c, in, out, batch, t);
 #define PIPE(NN) case NN: if constexpr (sizeof(T) == 4) { if (!getenv("JDSP_FFT_NO_PIPE")) return launch_c2c_pipe<NN, INV>(c, (const cx<float> *)in, (cx<float> *)out, batch, (const cx<float> *)t); } return launch_c2c_small<T, NN, INV>(c, in, out, batch, t);
-        SMALL(2) SMALL(4) SMALL(8) SMALL(16) SMALL(32) SMALL(64) SMALL(128) SMALL(256) SMALL(512) SMALL(1024) PIPE(2048) PIPE(4096) PIPE(8192)
+        SMALL(2) SMALL(4) SMALL(8) SMALL(16) SMALL(32) SMALL(64) SMALL(128) SMALL(256) SMALL(512) SMALL(1024) PIPE(2048) PIPE(4096)
 #undef PIPE
 #undef SMALL
         case 16384:
-            if constexpr (sizeof(T) == 4) { if (getenv("JDSP_FFT_ONCHIP16K")) return launch_c2c_small<T, 16384, INV>(c, in, out, batch, t); }
+            if constexpr (sizeof(T) == 4) { if (!getenv("JDSP_FFT_NO_BIG")) return launch_c2c_big<16384, INV>(c, (const cx<float> *)in, (cx<float> *)out, batch); }
             if constexpr (sizeof(T) == 4) { if (getenv("JDSP_FFT_FUSED")) return launch_c2c_fused<64, 256, INV>(c, in, out, batch); }
             return launch_c2c_fourstep<T, 64, 256, INV>(c, in, out, batch, tkind);
         case 32768:

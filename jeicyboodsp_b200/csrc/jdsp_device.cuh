@@ -136,17 +136,50 @@ template <bool INV, typename T> JDSP_DEV void dft16(cx<T> (&a)[16]) {
     t = a[7]; a[7] = a[13]; a[13] = t;
     t = a[11]; a[11] = a[14]; a[14] = t;
 }
+// multiply by exp(-+ 2*pi*j * m/32), m = 1..15 odd handled generally (even m go through cw16)
+template <bool INV, int M, typename T> JDSP_DEV cx<T> cw32(cx<T> a) {
+    if constexpr (M % 2 == 0) return cw16<INV, M / 2>(a);
+    else {
+        // cos / sin of 2*pi*m/32 for m = 1, 3, 5, 7, 9, 11, 13, 15
+        constexpr double C[8] = {0.98078528040323044913, 0.83146961230254523708, 0.55557023301960222474, 0.19509032201612826785,
+                                 -0.19509032201612826785, -0.55557023301960222474, -0.83146961230254523708, -0.98078528040323044913};
+        constexpr double S[8] = {0.19509032201612826785, 0.55557023301960222474, 0.83146961230254523708, 0.98078528040323044913,
+                                 0.98078528040323044913, 0.83146961230254523708, 0.55557023301960222474, 0.19509032201612826785};
+        const T wr = (T)C[M / 2], wi = (T)-S[M / 2];   // forward twiddle exp(-2*pi*j*m/32)
+        return cmulw(a, wr, INV ? -wi : wi);
+    }
+}
+// 32 points as two interleaved DFT-16s (even / odd samples) and one twiddled radix-2 layer; natural order in and out.
+template <bool INV, typename T> JDSP_DEV void dft32(cx<T> (&a)[32]) {
+    cx<T> e[16], o[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { e[i] = a[2 * i]; o[i] = a[2 * i + 1]; }
+    dft16<INV>(e);
+    dft16<INV>(o);
+    o[1] = cw32<INV, 1>(o[1]); o[2] = cw32<INV, 2>(o[2]); o[3] = cw32<INV, 3>(o[3]); o[4] = cw32<INV, 4>(o[4]);
+    o[5] = cw32<INV, 5>(o[5]); o[6] = cw32<INV, 6>(o[6]); o[7] = cw32<INV, 7>(o[7]); o[8] = cw32<INV, 8>(o[8]);
+    o[9] = cw32<INV, 9>(o[9]); o[10] = cw32<INV, 10>(o[10]); o[11] = cw32<INV, 11>(o[11]); o[12] = cw32<INV, 12>(o[12]);
+    o[13] = cw32<INV, 13>(o[13]); o[14] = cw32<INV, 14>(o[14]); o[15] = cw32<INV, 15>(o[15]);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { a[k] = cadd(e[k], o[k]); a[k + 16] = csub(e[k], o[k]); }
+}
 template <int R, bool INV, typename T> JDSP_DEV void dftR(cx<T> (&a)[R]) {
     if constexpr (R == 2) dft2<INV>(a[0], a[1]);
     else if constexpr (R == 4) dft4<INV>(a[0], a[1], a[2], a[3]);
     else if constexpr (R == 8) dft8<INV>(a);
     else if constexpr (R == 16) dft16<INV>(a);
+    else if constexpr (R == 32) dft32<INV>(a);
     else static_assert(R == 1, "unsupported radix");
 }
 
 // ---- padded shared-memory layout: one spare element every 16 keeps radix-16 strides conflict-free
 JDSP_DEV int pad16(int e) { return e + (e >> 4); }
 __host__ __device__ constexpr int padded_len(int n) { return n + (n >> 4); }
+// With E points per thread the first pass writes runs of E consecutive elements per thread: one spare element per E
+// (E = 32) keeps those stride-E stores conflict-free the way one per 16 does for E <= 16.
+template <int E> struct PadOf { static constexpr int SHIFT = E >= 32 ? 5 : 4; };
+template <int E> JDSP_DEV int padE(int e) { return e + (e >> PadOf<E>::SHIFT); }
+template <int E> __host__ __device__ constexpr int padded_len_e(int n) { return n + (n >> PadOf<E>::SHIFT); }
 
 template <int SYNC> JDSP_DEV void group_sync() {
     if constexpr (SYNC == 0) __syncwarp(); else __syncthreads();
@@ -194,50 +227,59 @@ JDSP_DEV void fft_pass_compute(cx<T> (&reg)[E], int t, const cx<T> *__restrict__
         for (int i = 0; i < R; ++i) reg[u + i * U] = v[i];
     }
 }
-// Padded addresses with compile-time strides: for a stride S that is a multiple of 16,
-// pad16(b + i*S) == pad16(b) + i*(S + S/16); for b a multiple of 16 and i < 16, pad16(b + i) == pad16(b) + i.
+// Padded addresses with compile-time strides (P = 2^SHIFT = 16, or 32 when E = 32): for a stride S that is a multiple of P,
+// pad(b + i*S) == pad(b) + i*(S + S/P); for b a multiple of P and i < P, pad(b + i) == pad(b) + i; for b < S with S a
+// divisor of P, pad(b + i*S) == b + i*S + (i*S)/P.
 // scatter the outputs of a non-final pass to their Stockham positions (padded)
 template <typename T, int NC, int E, int R, int NS>
 JDSP_DEV void fft_pass_store(const cx<T> (&reg)[E], int t, cx<T> *buf) {
-    constexpr int G = NC / E, U = E / R;
+    constexpr int G = NC / E, U = E / R, P = 1 << PadOf<E>::SHIFT;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         const int j = t + G * u, k = j & (NS - 1);
         const int base = (j - k) * R + k;
-        if constexpr (NS % 16 == 0) {
-            cx<T> *p = buf + pad16(base);
+        if constexpr (NS % P == 0) {
+            cx<T> *p = buf + padE<E>(base);
 #pragma unroll
-            for (int i = 0; i < R; ++i) p[i * (NS + NS / 16)] = reg[u + i * U];
-        } else if constexpr (NS == 1 && R == 16) {
-            cx<T> *p = buf + pad16(base);  // base = 16*j
+            for (int i = 0; i < R; ++i) p[i * (NS + NS / P)] = reg[u + i * U];
+        } else if constexpr (NS == 1 && R == P) {
+            cx<T> *p = buf + padE<E>(base);  // base = P*j
 #pragma unroll
             for (int i = 0; i < R; ++i) p[i] = reg[u + i * U];
         } else {
 #pragma unroll
-            for (int i = 0; i < R; ++i) buf[pad16(base + i * NS)] = reg[u + i * U];
+            for (int i = 0; i < R; ++i) buf[padE<E>(base + i * NS)] = reg[u + i * U];
         }
     }
 }
 template <typename T, int NC, int E> JDSP_DEV void fft_load_regs(cx<T> (&reg)[E], int t, const cx<T> *buf) {
-    constexpr int G = NC / E;
-    if constexpr (G % 16 == 0) {
-        const cx<T> *p = buf + pad16(t);
+    constexpr int G = NC / E, P = 1 << PadOf<E>::SHIFT;
+    if constexpr (G % P == 0) {
+        const cx<T> *p = buf + padE<E>(t);
 #pragma unroll
-        for (int m = 0; m < E; ++m) reg[m] = p[m * (G + G / 16)];
+        for (int m = 0; m < E; ++m) reg[m] = p[m * (G + G / P)];
+    } else if constexpr (G < P && P % G == 0) {
+        const cx<T> *p = buf + t;   // t < G <= P/2: no pad below t
+#pragma unroll
+        for (int m = 0; m < E; ++m) reg[m] = p[G * m + (G * m) / P];
     } else {
 #pragma unroll
-        for (int m = 0; m < E; ++m) reg[m] = buf[pad16(t + G * m)];
+        for (int m = 0; m < E; ++m) reg[m] = buf[padE<E>(t + G * m)];
     }
 }
 template <typename T, int NC, int E> JDSP_DEV void fft_store_regs(const cx<T> (&reg)[E], int t, cx<T> *buf) {
-    constexpr int G = NC / E;
-    if constexpr (G % 16 == 0) {
-        cx<T> *p = buf + pad16(t);
+    constexpr int G = NC / E, P = 1 << PadOf<E>::SHIFT;
+    if constexpr (G % P == 0) {
+        cx<T> *p = buf + padE<E>(t);
 #pragma unroll
-        for (int m = 0; m < E; ++m) p[m * (G + G / 16)] = reg[m];
+        for (int m = 0; m < E; ++m) p[m * (G + G / P)] = reg[m];
+    } else if constexpr (G < P && P % G == 0) {
+        cx<T> *p = buf + t;
+#pragma unroll
+        for (int m = 0; m < E; ++m) p[G * m + (G * m) / P] = reg[m];
     } else {
 #pragma unroll
-        for (int m = 0; m < E; ++m) buf[pad16(t + G * m)] = reg[m];
+        for (int m = 0; m < E; ++m) buf[padE<E>(t + G * m)] = reg[m];
     }
 }
 

@@ -86,7 +86,7 @@ template <typename T> static std::vector<cx<T>> pass_twiddles(int n, int emax = 
 // kind 0: float pass twiddles for length n     kind 1: double pass twiddles
 // kind 2: float2 (cos, sin)(2*pi*k/(2n)), k<=n/2   (real-FFT post-twiddle for packed length n)
 // kind 3/4: float/double flat exp(-2*pi*j*q/n), q<n (four-step inter-stage twiddle)
-// kind 5: float pass twiddles for length n with 8 points per thread
+// kind 5: float pass twiddles for length n with 8 points per thread     kind 6: with 32 points per thread
 static int get_table(jdsp_ctx *c, int kind, int n, void **out) {
     auto key = std::make_pair(kind, n);
     auto it = c->tables.find(key);
@@ -94,8 +94,8 @@ static int get_table(jdsp_ctx *c, int kind, int n, void **out) {
     void *d = nullptr;
     if (kind == 0) {
         cx<float> *p; TRY(upload(c, pass_twiddles<float>(n), &p)); d = p;
-    } else if (kind == 5) {
-        cx<float> *p; TRY(upload(c, pass_twiddles<float>(n, 8), &p)); d = p;
+    } else if (kind == 5 || kind == 6) {
+        cx<float> *p; TRY(upload(c, pass_twiddles<float>(n, kind == 5 ? 8 : 32), &p)); d = p;
     } else if (kind == 1) {
         cx<double> *p; TRY(upload(c, pass_twiddles<double>(n), &p)); d = p;
     } else if (kind == 3) {

@@ -10,6 +10,16 @@
 
 namespace jdsp {
 
+// Pull a 128-byte line into L2 ahead of use: costs no registers and no shared memory, so kernels whose CTAs alternate
+// between a load phase and a compute phase can keep HBM busy during the compute phase.
+JDSP_DEV void prefetch_l2(const void *p) {
+#ifndef JDSP_EMUL
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 template <int N> struct FftGeom {
     static constexpr int E = N < 16 ? N : 16;     // complex points per thread
     static constexpr int G = N / E;               // threads per transform
@@ -101,9 +111,11 @@ fft_c2c_kernel(const cx<T> *__restrict__ in, cx<T> *__restrict__ out, long batch
 // current one into registers, so HBM reads overlap all passes and the stores of the current transform.  Without this a
 // CTA alternates between a load phase and a compute phase, and the few resident CTAs per SM (register-heavy 256/512-
 // thread groups) do not cover each other's gaps (measured: 0.71 / 0.45 of the HBM copy rate at N = 4096 / 8192).
-template <int N> struct FftPipeGeom {
-    static constexpr int E = 16, G = N / E, THREADS = G;
-    static constexpr int PADN = padded_len(N);
+template <int N, int E_ = (N >= 8192 ? 32 : 16)> struct FftPipeGeom {
+    // 32 points per thread at N = 8192: passes 32 x 32 x 8 (two shared-memory exchanges) instead of 16 x 16 x 16 x 2 (three);
+    // the exchanges, not HBM, bound this size (one 512-thread CTA per SM moved 393 KB through shared memory per transform)
+    static constexpr int E = E_, G = N / E, THREADS = G;
+    static constexpr int PADN = padded_len_e<E>(N);
     static constexpr size_t OFF_EXCH = (size_t)N * sizeof(cx<float>);
     static constexpr size_t OFF_BAR = OFF_EXCH + (size_t)PADN * sizeof(cx<float>);
     static constexpr size_t SMEM = OFF_BAR + 16;
@@ -150,6 +162,53 @@ fft_c2c_pipe_kernel(const cx<float> *__restrict__ in, cx<float> *__restrict__ ou
     }
 }
 
+// ---- N = 16384, fp32, on chip: 512 threads x 32 points (passes 32 x 32 x 16), one CTA per SM, points straight between
+// global memory and registers; one HBM read + one write instead of the four-step's two round trips.
+template <int N> struct FftBigGeom {
+    static constexpr int E = 32, G = N / E, THREADS = G;
+    static constexpr int PADN = padded_len_e<E>(N);
+    static constexpr size_t SMEM = (size_t)PADN * sizeof(cx<float>);
+    static_assert(G <= 1024, "one CTA per transform");
+};
+template <int N, bool INV>
+__global__ void __launch_bounds__(FftBigGeom<N>::THREADS, N >= 16384 ? 1 : 2)
+fft_c2c_big_kernel(const cx<float> *__restrict__ in, cx<float> *__restrict__ out, long batch, const cx<float> *__restrict__ tw, float scale) {
+    using Geo = FftBigGeom<N>;
+    constexpr int E = Geo::E, G = Geo::G;
+    JDSP_DYN_SMEM(smem_raw);
+    cx<float> *exch = reinterpret_cast<cx<float> *>(smem_raw);
+    const int t = threadIdx.x;
+    for (long f = blockIdx.x; f < batch; f += gridDim.x) {
+        cx<float> reg[E];
+        const cx<float> *src = in + f * N + t;
+#pragma unroll
+        for (int m = 0; m < E; ++m) reg[m] = src[G * m];
+        __syncthreads();   // the previous transform is done with the exchange buffer
+        {   // pull the NEXT transform into L2 while this one is computed (no registers, no shared memory): its loads then
+            // see L2 latency and bandwidth instead of HBM's
+            const long fn = f + gridDim.x;
+            if (fn < batch) {
+                const char *nx = reinterpret_cast<const char *>(in + fn * N);
+#pragma unroll
+                for (int i = 0; i < (int)(N * sizeof(cx<float>) / 128 / G); ++i) prefetch_l2(nx + ((long)t + (long)G * i) * 128);
+            }
+        }
+        const cx<float> *twp = tw;
+#ifndef JDSP_EMUL
+        // the read-only twiddle loads of the later passes would otherwise be hoisted next to the 32 data loads (31 more
+        // register pairs -> 280 bytes of spills): hide the pointer until the data has landed
+        asm volatile("" : "+l"(twp)::"memory");
+#endif
+        group_fft<float, N, E, INV, 1>(reg, t, exch, twp);
+        cx<float> *dst = out + f * N + t;
+#pragma unroll
+        for (int m = 0; m < E; ++m) { reg[m].x *= scale; reg[m].y *= scale; dst[G * m] = reg[m]; }
+#ifndef JDSP_EMUL
+        asm volatile("" ::: "memory");   // and keep the next transform's loads below these stores
+#endif
+    }
+}
+
 // ---- four-step for N = N1 * N2 (both handled by one thread group each) -----------------------------------
 // Step A: for CT adjacent columns n2, DFT over n1 (stride N2), multiply by W_N^(n2*k1), write row-major [k1][n2].
 // Global accesses are CT*sizeof(cx) contiguous bytes per row; all loads of a tile are issued before the first
@@ -182,6 +241,15 @@ fft_cols_kernel(const cx<T> *__restrict__ in, cx<T> *__restrict__ tmp, int N2, l
         // twiddles W_N^((c0+c)*k1), k1 = t + G*m: three exact table reads, the rest by short products (depth <= 4)
         const long col = c0 + c;
         const cx<T> wa = twN[col * t], b1 = twN[col * G], b4 = twN[col * (4 * G)];
+        {   // next tile of this CTA -> L2 (row segments of CT values: CT*sizeof(cx)/128 lines per row)
+            const long nt = tile + gridDim.x;
+            if (nt < n_tiles) {
+                constexpr int LPR = (CT * (int)sizeof(cx<T>) + 127) / 128;
+                const cx<T> *nsrc = in + (nt / tiles_per_fft) * N + (int)(nt % tiles_per_fft) * CT;
+                for (int i = threadIdx.x; i < N1 * LPR; i += THREADS)
+                    prefetch_l2(reinterpret_cast<const char *>(nsrc + (long)(i / LPR) * N2) + (i % LPR) * 128);
+            }
+        }
         __syncthreads();  // previous tile has been written out of shared memory
 #pragma unroll
         for (int i = 0; i < PER; ++i) sm[sc * PADN + pad16(sr + (THREADS / CT) * i)] = st[i];
@@ -242,6 +310,13 @@ fft_rows_kernel(const cx<T> *__restrict__ tmp, cx<T> *__restrict__ out, int N1, 
 #pragma unroll
         for (int m = 0; m < E; ++m) reg[m] = src[G * m];
         cx<T> *buf = sm + r * PADN;
+        {   // next tile of this CTA -> L2 (RT adjacent rows are one contiguous run)
+            const long nt = tile + gridDim.x;
+            if (nt < n_tiles) {
+                const char *nsrc = reinterpret_cast<const char *>(tmp + (nt / tiles_per_fft) * N + (long)((int)(nt % tiles_per_fft) * RT) * N2);
+                for (int i = threadIdx.x; i < (int)(RT * N2 * sizeof(cx<T>) / 128); i += THREADS) prefetch_l2(nsrc + (long)i * 128);
+            }
+        }
         __syncthreads();  // previous tile has been written out of shared memory
         group_fft<T, N2, E, INV, 0>(reg, t, buf, tw2);
         group_sync<0>();
