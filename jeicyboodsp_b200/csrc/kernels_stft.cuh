@@ -62,10 +62,12 @@ struct RoundtripArgs {
 
 template <int N>
 struct RoundtripGeom {
+    // 16 points per thread.  32 per thread (one exchange instead of two at N = 512 / 1024) was measured 4-12 % SLOWER here:
+    // half the threads per transform at 94 registers lowers occupancy more than the saved exchange gains.
     static constexpr int E = 16, G = N / E, SYNC = G > 32 ? 1 : 0;
     static constexpr int FPB = G >= 128 ? 1 : 128 / G;  // block pairs per CTA
     static constexpr int THREADS = FPB * G;
-    static constexpr int PADN = padded_len(N);
+    static constexpr int PADN = padded_len_e<E>(N);
     static constexpr size_t SMEM = (size_t)FPB * PADN * sizeof(cf) + (size_t)FPB * 2 * N * sizeof(int16_t);
 };
 
