@@ -215,8 +215,7 @@ struct MfccGeom {
                                                      // cross-frame reads of the mel stage hit different banks
     static constexpr size_t OFF_FBUF = 0;
     static constexpr size_t OFF_MEL = OFF_FBUF + ((((size_t)F * FP * sizeof(cf)) + 15) & ~(size_t)15);
-    static constexpr size_t OFF_MELW = OFF_MEL + (size_t)F * MAXMEL * sizeof(float);       // [2][NC]: 1-w, w
-    static constexpr size_t OFF_DCT = OFF_MELW + (size_t)2 * NC * sizeof(float);          // [n_mel][16] (cepstrum index fastest)
+    static constexpr size_t OFF_DCT = OFF_MEL + (size_t)F * MAXMEL * sizeof(float);        // [n_mel][16] (cepstrum index fastest)
     static constexpr size_t OFF_START = OFF_DCT + (size_t)MAXMEL * 16 * sizeof(float);     // [MAXMEL+2]
     static constexpr size_t OFF_WINH = OFF_START + (size_t)(MAXMEL + 8) * sizeof(int);     // [N] half window (zero past frame_len)
     static constexpr size_t OFF_BAR = OFF_WINH + (size_t)N * sizeof(float);
@@ -236,7 +235,6 @@ __global__ void __launch_bounds__(MfccGeom<NC>::NT) mfcc_kernel(MfccArgs a) {
     JDSP_DYN_SMEM(smem_raw);
     cf *fbuf = reinterpret_cast<cf *>(smem_raw + Geo::OFF_FBUF);
     float *mel = reinterpret_cast<float *>(smem_raw + Geo::OFF_MEL);
-    float *melw = reinterpret_cast<float *>(smem_raw + Geo::OFF_MELW);
     float *dct = reinterpret_cast<float *>(smem_raw + Geo::OFF_DCT);
     int *mstart = reinterpret_cast<int *>(smem_raw + Geo::OFF_START);
     float *winh = reinterpret_cast<float *>(smem_raw + Geo::OFF_WINH);
@@ -248,17 +246,18 @@ __global__ void __launch_bounds__(MfccGeom<NC>::NT) mfcc_kernel(MfccArgs a) {
     const cf *tw = a.tw;
     const size_t span_b = Geo::span_bytes(W, hop);
     int16_t *xsb = reinterpret_cast<int16_t *>(smem_raw + Geo::OFF_XS);
-    for (int i = tid; i < NC; i += NT) { const float w = a.mel_w[i]; melw[i] = 1.f - w; melw[NC + i] = w; }
     for (int i = tid; i < NCEP * C; i += NT) dct[(i % C) * DP + (i / C)] = a.dct[i];
     for (int i = tid; i < C + 2; i += NT) mstart[i] = a.mel_start[i];
     for (int i = tid; i < 2 * NC; i += NT) winh[i] = i < W ? a.win_half[i] : 0.f;
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
-    float tc[SPT], ts[SPT];
+    float tc[SPT], ts[SPT], wk[SPT], wm[SPT];   // untangle twiddle and the filterbank weight (rgdFilterBank, :139-150) of bins k and NC-k
 #pragma unroll
     for (int qq = 0; qq < SPT; ++qq) {
         const int k = tid + qq * NT;
         const float2 w = (k < NSLOT) ? a.twr[k] : make_float2(1.f, 0.f);
         tc[qq] = w.x; ts[qq] = w.y;
+        wk[qq] = (k < NC) ? a.mel_w[k] : 0.f;
+        wm[qq] = (k > 0 && k < NSLOT) ? a.mel_w[NC - k] : 0.f;
     }
     const long tiles_per_utt = (n_frames + F - 1) / F;
     const long n_tiles = a.n_utts * tiles_per_utt;
@@ -320,22 +319,30 @@ __global__ void __launch_bounds__(MfccGeom<NC>::NT) mfcc_kernel(MfccArgs a) {
                     cf *fb = fbuf + f * FP;
                     cf X1, X2;
                     untangle2x(fb[pk], fb[pm], wc, wsn, X1, X2);
-                    if (k > 0 && k < NC - k) fb[pm].x = sqrt_fast(X2.x * X2.x + X2.y * X2.y);   // bin NC-k
-                    fb[pk].x = sqrt_fast(X1.x * X1.x + X1.y * X1.y);                             // bin k (bin NC itself is unused)
+                    // each bin feeds two neighbouring channels with (1-w)|X| and w|X| (:157-168): store both shares in place
+                    if (k > 0 && k < NC - k) {                                                    // bin NC-k
+                        const float a2 = sqrt_fast(X2.x * X2.x + X2.y * X2.y);
+                        fb[pm] = cmake<float>(a2 - wm[qq] * a2, wm[qq] * a2);
+                    }
+                    const float a1 = sqrt_fast(X1.x * X1.x + X1.y * X1.y);                        // bin k (bin NC itself is unused)
+                    fb[pk] = cmake<float>(a1 - wk[qq] * a1, wk[qq] * a1);
                 }
             }
         }
         __syncthreads();  // (D)
-        // ---- M3 MelFilterBank (:154-174): channel c collects (1-w)*a over bins with index c and w*a over index c+1.
-        // Item = (channel, frame) with the frame fastest, so the lanes of a warp walk 4 neighbouring channels of
-        // similar width.
+        // ---- M3 MelFilterBank (:154-174): channel c collects the (1-w) shares of the bins with index c and the w shares of
+        // the bins with index c+1.  Item = (channel, frame) with the frame fastest, so the lanes of a warp walk 4 neighbouring
+        // channels of similar width.  (Measured and rejected: pairing channel p with C-1-p for equal work per thread and
+        // splitting the walk into pad-free runs with four running sums -- 25 % SLOWER, the extra branches diverge.)
         for (int it = tid; it < C * F; it += NT) {
             const int c = it / F, f = it % F;
             const int i0 = mstart[c], i1 = mstart[c + 1], i2 = mstart[c + 2];
             const cf *mg = fbuf + f * FP;
             float acc = 0.f;
-            for (int i = i0; i < i1; ++i) acc = fmaf(melw[i], mg[pad16(i)].x, acc);
-            for (int i = i1; i < i2; ++i) acc = fmaf(melw[NC + i], mg[pad16(i)].x, acc);
+#pragma unroll 4
+            for (int i = i0; i < i1; ++i) acc += mg[pad16(i)].x;
+#pragma unroll 4
+            for (int i = i1; i < i2; ++i) acc += mg[pad16(i)].y;
             mel[f * MAXMEL + c] = logf(acc);  // :170-172
         }
         __syncthreads();  // (E)
@@ -344,8 +351,11 @@ __global__ void __launch_bounds__(MfccGeom<NC>::NT) mfcc_kernel(MfccArgs a) {
             const int f = it / NCEP, i = it % NCEP;
             const float *ml = mel + f * MAXMEL;
             float acc = 0.f;
-            for (int c = 0; c < C; ++c) acc = fmaf(dct[c * DP + i], ml[c], acc);
-            a.feat[u * feat_pitch + (t0 + f) * NCEP + i] = acc;
+            float acc1 = 0.f;
+            int c = 0;
+            for (; c + 2 <= C; c += 2) { acc = fmaf(dct[c * DP + i], ml[c], acc); acc1 = fmaf(dct[(c + 1) * DP + i], ml[c + 1], acc1); }
+            if (c < C) acc = fmaf(dct[c * DP + i], ml[c], acc);
+            a.feat[u * feat_pitch + (t0 + f) * NCEP + i] = acc + acc1;
         }
         cur ^= 1;
     }

@@ -146,6 +146,8 @@ static inline float2 __fadd2_rn(float2 a, float2 b) { return {a.x + b.x, a.y + b
 static inline float2 __fmul2_rn(float2 a, float2 b) { return {a.x * b.x, a.y * b.y}; }
 static inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return {fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __clz(unsigned x) { return x ? __builtin_clz(x) : 32; }
 static inline unsigned __brev(unsigned x) {
