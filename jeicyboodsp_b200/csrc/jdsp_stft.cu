@@ -211,17 +211,15 @@ static int denoise_launch_slice(jdsp_ctx *c, jdsp_denoise_state *st, cudaStream_
                                 uint8_t *d_vad) {
     const jdsp_denoise_params &p = st->p;
     const long NC = p.n_fft / 2, H = p.hop;
-    void *tw, *twr, *tw8 = nullptr;
+    void *tw, *twr;
     TRY(get_table(c, 0, (int)NC, &tw));
     TRY(get_table(c, 2, (int)NC, &twr));
     const char *force = getenv("JDSP_DENOISE_KERNEL");
-    const bool e8 = p.n_fft == 512 && getenv("JDSP_STREAM_E8");   // experiment: a warp per stream, 8 points per thread
-    if (e8) TRY(get_table(c, 5, (int)NC, &tw8));
     const long wave = p.n_fft == 512 ? denoise_stream_wave<256>(c) : denoise_stream_wave<512>(c);
     long n_tile = n % wave, n_main = n - n_tile;
     if (n_tile * 16 >= wave * 7) { n_main = n; n_tile = 0; }
     if (force && !strcmp(force, "tile")) { n_main = 0; n_tile = n; }
-    if ((force && !strcmp(force, "stream")) || e8) { n_main = n; n_tile = 0; }
+    if (force && !strcmp(force, "stream")) { n_main = n; n_tile = 0; }
     auto slice = [&](long s0, long cnt) {
         DenoiseArgs a;
         const long g0 = stream0 + s0;   // index into the state arrays
@@ -241,9 +239,8 @@ static int denoise_launch_slice(jdsp_ctx *c, jdsp_denoise_state *st, cudaStream_
     c->stream = stream;
     int rc = JDSP_OK;
     if (n_main > 0) {
-        DenoiseArgs a = slice(0, n_main);
-        if (e8) { a.tw = (const cf *)tw8; rc = launch_denoise_stream<256, 8>(c, a, p.mode); }
-        else rc = (p.n_fft == 512) ? launch_denoise_stream<256>(c, a, p.mode) : launch_denoise_stream<512>(c, a, p.mode);
+        const DenoiseArgs a = slice(0, n_main);
+        rc = (p.n_fft == 512) ? launch_denoise_stream<256>(c, a, p.mode) : launch_denoise_stream<512>(c, a, p.mode);
     }
     if (rc == JDSP_OK && n_tile > 0) {
         const DenoiseArgs a = slice(n_main, n_tile);

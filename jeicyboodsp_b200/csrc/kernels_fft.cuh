@@ -214,7 +214,7 @@ fft_c2c_big_kernel(const cx<float> *__restrict__ in, cx<float> *__restrict__ out
 // Global accesses are CT*sizeof(cx) contiguous bytes per row; all loads of a tile are issued before the first
 // shared-memory store so a CTA keeps its whole tile in flight.
 template <typename T, int N1, int CT, bool INV>
-__global__ void __launch_bounds__(CT * FftGeom<N1>::G, sizeof(T) == 4 ? (CT * FftGeom<N1>::G >= 512 ? 2 : 3) : 1)
+__global__ void __launch_bounds__(CT * FftGeom<N1>::G, sizeof(T) == 4 ? (CT * FftGeom<N1>::G >= 512 ? 2 : 768 / (CT * FftGeom<N1>::G)) : 1)
 fft_cols_kernel(const cx<T> *__restrict__ in, cx<T> *__restrict__ tmp, int N2, long n_fft, const cx<T> *__restrict__ tw1,
                 const cx<T> *__restrict__ twN) {
     using Geo = FftGeom<N1>;
@@ -287,7 +287,7 @@ fft_cols_kernel(const cx<T> *__restrict__ in, cx<T> *__restrict__ tmp, int N2, l
 // Step B: for RT adjacent rows k1 of [k1][n2], DFT over n2 (contiguous rows: straight into registers), then a
 // shared-memory transpose so that X[k1 + N1*k2] leaves in runs of RT consecutive values.
 template <typename T, int N2, int RT, bool INV>
-__global__ void __launch_bounds__(RT * FftGeom<N2>::G, sizeof(T) == 4 ? (RT * FftGeom<N2>::G >= 512 ? 2 : 3) : 1)
+__global__ void __launch_bounds__(RT * FftGeom<N2>::G, sizeof(T) == 4 ? (RT * FftGeom<N2>::G >= 512 ? 2 : 768 / (RT * FftGeom<N2>::G)) : 1)
 fft_rows_kernel(const cx<T> *__restrict__ tmp, cx<T> *__restrict__ out, int N1, long n_fft, const cx<T> *__restrict__ tw2, T scale) {
     using Geo = FftGeom<N2>;
     constexpr int E = Geo::E, G = Geo::G, THREADS = RT * G;

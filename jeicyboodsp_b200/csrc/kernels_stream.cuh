@@ -21,6 +21,8 @@ struct StreamGeom {
     static constexpr int N = 2 * NC, H = NC, E = E_, G = NC / E, NT = 64, GPC = NT / G;
     // Registers are allocated per SM sub-partition (16K each): 128/thread keeps 4 warps per scheduler, i.e. 8 CTAs (32 streams)
     // per SM, so that 4096 streams are ONE wave on 148 SMs; 144 would drop to 3 warps per scheduler and a 15 % second wave.
+    // (8 points per thread x 32 threads per stream -- E_ = 8, twice the warps, 96 registers -- was measured 6 % slower: its
+    // three-pass transforms move 321 instead of 200 shared-memory wavefronts per frame and stall on the MIO queue.)
     static constexpr int MAXREG = E == 16 ? 128 : 96;
     // Second-pass twiddles rebuilt from four seeds instead of 15 table loads: 13 % fewer shared-memory wavefronts, 3 % more
     // instructions -- measured 2 % SLOWER (the kernel is bound by per-warp issue latency at 3.5 warps per scheduler, not by
