@@ -393,7 +393,7 @@ template <typename T> JDSP_DEV void st_hint(cx<T> *p, cx<T> v, uint64_t) { *p = 
 
 template <typename T, int N1, int N2, bool INV>
 struct FusedGeom {
-    static constexpr int THREADS = 512;
+    static constexpr int THREADS = 256;
     static constexpr int G1 = FftGeom<N1>::G, G2 = FftGeom<N2>::G, E = 16;
     static constexpr int CT = THREADS / G1, RT = THREADS / G2;      // columns per column tile, rows per row tile
     static constexpr int TA = N2 / CT, TB = N1 / RT;                // tiles per transform
@@ -404,7 +404,7 @@ struct FusedGeom {
     static_assert(TA >= 1 && TB >= 1 && N2 % CT == 0 && N1 % RT == 0, "tiles must divide the transform");
 };
 template <typename T, int N1, int N2, bool INV>
-__global__ void __launch_bounds__(512, 2)
+__global__ void __launch_bounds__(256, 3)
 fft_fourstep_fused_kernel(const cx<T> *__restrict__ in, cx<T> *tmp, cx<T> *__restrict__ out, long batch, int look, int ring,
                           const cx<T> *__restrict__ tw1, const cx<T> *__restrict__ tw2, const cx<T> *__restrict__ twN, T scale,
                           FusedFftSync sy) {
