@@ -130,6 +130,27 @@ __global__ void __launch_bounds__(RoundtripGeom<N>::THREADS) roundtrip_kernel(Ro
     }
 }
 
+// One spectral bin of D2 + D3/D4, shared by both denoise kernels so that they produce identical bits: noise average /
+// publish (:182-193), then Y = gain * X with the 1/N of the inverse transform folded into the gain.  nss holds ns/N (SS) or
+// ns^2/N (Wiener).  cbits: bit0 update, bit1 halve, bit2 publish.  UPD: 0 = never update, 1 = always, 2 = when cbits != 0.
+// X.x carries a +1e-15 bias so that X = 0 behaves like the reference's atan2(0,0) = 0: |X| - ns along +1 gives (-ns, 0)
+// (appendix C-7); the bias is below half an ulp of any non-zero bin of an int16 frame, so it changes nothing else.
+template <int MODE, int UPD>
+JDSP_DEV cf denoise_bin(cf X, unsigned cbits, float inv_n, float &avg, float &nss) {
+    X.x += 1e-15f;
+    const float p = X.x * X.x + X.y * X.y;
+    const float r = rsqrt_fast(fmaxf(p, 1e-30f));
+    if (UPD == 1 || (UPD == 2 && cbits != 0u)) {
+        avg += p * r;                                                      // :183  |X| = p * rsqrt(p)
+        if (cbits & 2u) avg *= 0.5f;                                       // :184-186
+        if (cbits & 4u) nss = (MODE == 0 ? avg : avg * avg) * inv_n;       // :189-193
+    }
+    float g;
+    if (MODE == 0) g = fmaf(-nss, r, inv_n);                               // amp = |X| - ns, no floor (:238)
+    else g = inv_n - fminf(nss * (r * r), inv_n);                          // WienerFilter_final.cpp:204-208
+    return cmake<float>(X.x * g, X.y * g);
+}
+
 // ================================================================================================
 // Denoise.  One CTA walks one stream in tiles of F consecutive frames (hop H = NC, frame N = 2*NC,
 // packed-real transform length NC).  Thread groups of G = NC/16 threads own one frame each for the
@@ -363,30 +384,10 @@ __global__ void __launch_bounds__(DenoiseGeom<NC, F>::NT, NC == 256 ? 6 : 3) den
                         cf *fb = fbuf + f * PADN;
                         cf X1, X2;
                         untangle2x(fb[pk], fb[pm], c, sn, X1, X2);
-                        const float p1 = X1.x * X1.x + X1.y * X1.y, p2 = X2.x * X2.x + X2.y * X2.y;
-                        const float r1 = rsqrt_fast(fmaxf(p1, 1e-30f)), r2 = rsqrt_fast(fmaxf(p2, 1e-30f));
                         const unsigned cbits = (ctl >> (3 * f)) & 7u;
-                        if (cbits) {
-                            avg1[q] += p1 * r1; avg2[q] += p2 * r2;                        // :183 (|X| = p * rsqrt(p), 0 when p = 0)
-                            if (cbits & 2u) { avg1[q] *= 0.5f; avg2[q] *= 0.5f; }          // :184-186
-                            if (cbits & 4u) {                                              // :189-193
-                                nss1[q] = (MODE == 0 ? avg1[q] : avg1[q] * avg1[q]) * inv_n;
-                                nss2[q] = (MODE == 0 ? avg2[q] : avg2[q] * avg2[q]) * inv_n;
-                            }
-                        }
-                        float g1, g2;
-                        if (MODE == 0) {  // amp = |X| - ns, no floor (:238); Y = amp * e^{j angle X}
-                            g1 = fmaf(-nss1[q], r1, inv_n); g2 = fmaf(-nss2[q], r2, inv_n);
-                        } else {          // amp = |X| * (1 - min(ns^2/|X|^2, 1))  (WienerFilter_final.cpp:204-208)
-                            g1 = inv_n - fminf(nss1[q] * (r1 * r1), inv_n);
-                            g2 = inv_n - fminf(nss2[q] * (r2 * r2), inv_n);
-                        }
-                        if (f == 0 && first_block) { g1 = 0.f; g2 = 0.f; }  // the very first block only primes the keep buffer (:211-216)
-                        cf Y1 = c2(__fmul2_rn(f2(X1), make_float2(g1, g1))), Y2 = c2(__fmul2_rn(f2(X2), make_float2(g2, g2)));
-                        if (MODE == 0) {  // |X| = 0: atan2(0,0) = 0, so the reference emits (-ns, 0) (appendix C-7); X = 0 made Y = 0 above
-                            if (p1 == 0.f && !(f == 0 && first_block)) Y1.x = -nss1[q];
-                            if (p2 == 0.f && !(f == 0 && first_block)) Y2.x = -nss2[q];
-                        }
+                        cf Y1 = denoise_bin<MODE, 2>(X1, cbits, inv_n, avg1[q], nss1[q]);
+                        cf Y2 = denoise_bin<MODE, 2>(X2, cbits, inv_n, avg2[q], nss2[q]);
+                        if (f == 0 && first_block) { Y1 = cmake<float>(0.f, 0.f); Y2 = Y1; }  // the very first block only primes the keep buffer (:211-216)
                         cf Zk, Zm;
                         retangle2x(Y1, Y2, c, sn, Zk, Zm);
                         fb[pk] = Zk;

@@ -57,36 +57,21 @@ JDSP_DEV void cp_async_wait_all() {
 #endif
 }
 
-// One spectral bin of D2 + D3/D4: noise average / publish (:182-193) when UPD, then Y = gain * X with the 1/N of the
-// inverse transform folded into the gain.  nss holds ns/N (SS) or ns^2/N (Wiener).  cbits: bit1 halve, bit2 publish.
-// X.x carries a +1e-15 bias so that X = 0 behaves like the reference's atan2(0,0) = 0: |X| - ns along +1 gives (-ns, 0)
-// (appendix C-7); the bias is below half an ulp of any non-zero bin of an int16 frame, so it changes nothing else.
-template <int MODE, bool UPD>
-JDSP_DEV cf denoise_bin(cf X, unsigned cbits, float inv_n, float &avg, float &nss) {
-    X.x += 1e-15f;
-    const float p = X.x * X.x + X.y * X.y;
-    const float r = rsqrt_fast(fmaxf(p, 1e-30f));
-    if (UPD) {
-        avg += p * r;                                                      // :183  |X| = p * rsqrt(p)
-        if (cbits & 2u) avg *= 0.5f;                                       // :184-186
-        if (cbits & 4u) nss = (MODE == 0 ? avg : avg * avg) * inv_n;       // :189-193
-    }
-    float g;
-    if (MODE == 0) g = fmaf(-nss, r, inv_n);                               // amp = |X| - ns, no floor (:238)
-    else g = inv_n - fminf(nss * (r * r), inv_n);                          // WienerFilter_final.cpp:204-208
-    return cmake<float>(X.x * g, X.y * g);
-}
-
 // Per-bin stage of one frame on the transform's own registers: bins k = t + G*m (m < 8) pair with NC-k held by the partner
-// thread (exchanged through mir[]); bin NC/2 (thread 0, m = 8) pairs with itself: X = 2 conj(A), Z' = 2 conj(Y).
+// thread (exchanged through mir[]); bin NC/2 (thread 0, m = 8) pairs with itself and goes through the very same formulas as
+// in the CTA-per-stream kernel (A = B, second output kept), so that the two kernels agree bit for bit.
 template <int MODE, bool UPD, int E, int G, int MSTRIDE, int NT>
-JDSP_DEV void denoise_bins(cf (&reg)[E], cf *mir, const float2 *twr_t, unsigned cbits, float inv_n,
+JDSP_DEV void denoise_bins(cf (&reg)[E], cf *mir, const float2 *twr_t, float2 cs_half, unsigned cbits, float inv_n,
                            float2 *avgp, float (&nss1)[E / 2], float (&nss2)[E / 2], float &avgS, float &nssS) {
-    constexpr int HM = E / 2;
+    constexpr int HM = E / 2, U = UPD ? 1 : 0;
     {
-        const cf Xs = cmake<float>(2.f * reg[HM].x, -2.f * reg[HM].y);
-        const cf Ys = denoise_bin<MODE, UPD>(Xs, cbits, inv_n, avgS, nssS);
-        reg[HM] = cmake<float>(2.f * Ys.x, -2.f * Ys.y);
+        cf X1, X2;
+        untangle2x(reg[HM], reg[HM], cs_half.x, cs_half.y, X1, X2);
+        float a2 = avgS, n2 = nssS;
+        const cf Y1 = denoise_bin<MODE, U>(X1, cbits, inv_n, avgS, nssS);
+        const cf Y2 = denoise_bin<MODE, U>(X2, cbits, inv_n, a2, n2);
+        cf Zk;
+        retangle2x(Y1, Y2, cs_half.x, cs_half.y, Zk, reg[HM]);
     }
 #pragma unroll
     for (int m = 0; m < HM; ++m) {
@@ -95,8 +80,8 @@ JDSP_DEV void denoise_bins(cf (&reg)[E], cf *mir, const float2 *twr_t, unsigned 
         untangle2x(reg[m], mir[-m * MSTRIDE], cs.x, cs.y, X1, X2);
         float2 av = make_float2(0.f, 0.f);
         if (UPD) av = avgp[m * NT];          // the averages live in shared memory: only noise blocks touch them
-        const cf Y1 = denoise_bin<MODE, UPD>(X1, cbits, inv_n, av.x, nss1[m]);
-        const cf Y2 = denoise_bin<MODE, UPD>(X2, cbits, inv_n, av.y, nss2[m]);
+        const cf Y1 = denoise_bin<MODE, U>(X1, cbits, inv_n, av.x, nss1[m]);
+        const cf Y2 = denoise_bin<MODE, U>(X2, cbits, inv_n, av.y, nss2[m]);
         if (UPD) avgp[m * NT] = av;
         cf Zm;
         retangle2x(Y1, Y2, cs.x, cs.y, reg[m], Zm);
@@ -250,8 +235,9 @@ __global__ void __maxnreg__((StreamGeom<NC, E_>::MAXREG)) denoise_stream_kernel(
         for (int m = HM; m < E; ++m) own[m * MSTRIDE] = reg[m];
         if (t == 0) buf[Geo::PADN] = reg[0];
         group_sync<0>();
-        if (cbits) denoise_bins<MODE, true, E, G, MSTRIDE, NT>(reg, mir, twr_t, cbits, inv_n, avgp, nss1, nss2, avgS, nssS);
-        else denoise_bins<MODE, false, E, G, MSTRIDE, NT>(reg, mir, twr_t, cbits, inv_n, avgp, nss1, nss2, avgS, nssS);
+        const float2 cs_half = twr[NC / 2];
+        if (cbits) denoise_bins<MODE, true, E, G, MSTRIDE, NT>(reg, mir, twr_t, cs_half, cbits, inv_n, avgp, nss1, nss2, avgS, nssS);
+        else denoise_bins<MODE, false, E, G, MSTRIDE, NT>(reg, mir, twr_t, cs_half, cbits, inv_n, avgp, nss1, nss2, avgS, nssS);
         group_sync<0>();
 #pragma unroll
         for (int m = HM + 1; m < E; ++m) reg[m] = own[m * MSTRIDE];

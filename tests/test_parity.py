@@ -239,6 +239,34 @@ def test_denoise_identity_property(be, dkernel):
     assert np.abs(got - expect).max() <= 1.0 + 1e-4 * 9000
 
 
+@pytest.mark.parametrize("preset", ["bench", "ref"])
+@pytest.mark.parametrize("mode", [SS, WIENER])
+def test_denoise_kernels_bit_identical(be, monkeypatch, preset, mode):
+    """The two denoise kernels share their per-bin arithmetic and transform core: same int16 AND same pre-cast floats,
+    bit for bit, including silent stretches (the |X| = 0 corner) and the carry state they leave behind.  So it does not
+    matter which kernel the stream-count rule picks, nor whether a call is split between them."""
+    p = be.L.denoise_params(preset, mode)
+    H, nb, S = p.hop, 70, 5
+    x = np.stack([synth.denoise_stream(80 + s, nb * H) for s in range(S)])
+    x[1, 20 * H:34 * H] = 0            # digital silence after the noise spectrum has been published
+    x[2, :] = 0
+    res = {}
+    for kernel in ("tile", "stream"):
+        monkeypatch.setenv("JDSP_DENOISE_KERNEL", kernel)
+        st = be.ctx.denoise_state(p, S)
+        outs, f32s = [], []
+        for b0, k in ((0, 37), (37, 33)):        # two calls: the state written by one call feeds the next
+            d_out, d_f32 = be.zeros((S, k * H), np.int16), be.zeros((S, k * H), np.float32)
+            em = st.run(be.to_dev(x[:, b0 * H:(b0 + k) * H]), k * H, k, d_out, k * H, d_f32, k * H, None)
+            outs.append(be.to_host(d_out)[:, : em * H].copy())
+            f32s.append(be.to_host(d_f32)[:, : em * H].copy())
+        res[kernel] = (np.concatenate(outs, axis=1), np.concatenate(f32s, axis=1), st.publish_counts().copy())
+        st.close()
+    assert np.array_equal(res["tile"][2], res["stream"][2])
+    assert np.array_equal(res["tile"][1].view(np.uint32), res["stream"][1].view(np.uint32))
+    assert np.array_equal(res["tile"][0], res["stream"][0])
+
+
 def test_denoise_wave_split_and_state_handover(be, oracle, monkeypatch):
     """More streams than one wave of the stream-group kernel: whole waves run on it, the small remainder on the CTA-per-
     stream kernel, both over slices of ONE state.  A second call (forced the other way round) continues every stream
