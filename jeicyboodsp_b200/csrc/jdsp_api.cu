@@ -107,7 +107,7 @@ static int launch_c2c_pipe(jdsp_ctx *c, const cx<float> *in, cx<float> *out, lon
     return launch_check(c);
 }
 
-// fp32 N = 8192 / 16384 on chip, 32 points per thread (JDSP_FFT_NO_BIG=1 falls back to the pipelined / four-step kernels)
+// fp32 N = 4096 / 8192 / 16384 on chip, 32 points per thread (JDSP_FFT_NO_BIG=1 falls back to the pipelined / four-step kernels)
 template <int N, bool INV>
 static int launch_c2c_big(jdsp_ctx *c, const cx<float> *in, cx<float> *out, long batch) {
     using Geo = FftBigGeom<N>;
@@ -204,12 +204,16 @@ static int fft_dispatch(jdsp_ctx *c, const cx<T> *in, cx<T> *out, int n, long ba
     const cx<T> *t = (const cx<T> *)tw;
     switch (n) {
 #define SMALL(NN) case NN: return launch_c2c_small<T, NN, INV>(c, in, out, batch, t);
+        case 4096:
+            if constexpr (sizeof(T) == 4) { if (!getenv("JDSP_FFT_NO_BIG")) return launch_c2c_big<4096, INV>(c, (const cx<float> *)in, (cx<float> *)out, batch); }
+            if constexpr (sizeof(T) == 4) { if (!getenv("JDSP_FFT_NO_PIPE")) return launch_c2c_pipe<4096, INV>(c, (const cx<float> *)in, (cx<float> *)out, batch, (const cx<float> *)t); }
+            return launch_c2c_small<T, 4096, INV>(c, in, out, batch, t);
         case 8192:
             if constexpr (sizeof(T) == 4) { if (!getenv("JDSP_FFT_NO_BIG")) return launch_c2c_big<8192, INV>(c, (const cx<float> *)in, (cx<float> *)out, batch); }
             if constexpr (sizeof(T) == 4) { if (!getenv("JDSP_FFT_NO_PIPE")) return launch_c2c_pipe<8192, INV>(c, (const cx<float> *)in, (cx<float> *)out, batch, (const cx<float> *)t); }
             return launch_c2c_small<T, 8192, INV>(c, in, out, batch, t);
 #define PIPE(NN) case NN: if constexpr (sizeof(T) == 4) { if (!getenv("JDSP_FFT_NO_PIPE")) return launch_c2c_pipe<NN, INV>(c, (const cx<float> *)in, (cx<float> *)out, batch, (const cx<float> *)t); } return launch_c2c_small<T, NN, INV>(c, in, out, batch, t);
-        SMALL(2) SMALL(4) SMALL(8) SMALL(16) SMALL(32) SMALL(64) SMALL(128) SMALL(256) SMALL(512) SMALL(1024) PIPE(2048) PIPE(4096)
+        SMALL(2) SMALL(4) SMALL(8) SMALL(16) SMALL(32) SMALL(64) SMALL(128) SMALL(256) SMALL(512) SMALL(1024) PIPE(2048)
 #undef PIPE
 #undef SMALL
         case 16384:

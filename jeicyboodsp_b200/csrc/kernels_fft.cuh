@@ -171,7 +171,7 @@ template <int N> struct FftBigGeom {
     static_assert(G <= 1024, "one CTA per transform");
 };
 template <int N, bool INV>
-__global__ void __launch_bounds__(FftBigGeom<N>::THREADS, N >= 16384 ? 1 : 2)
+__global__ void __launch_bounds__(FftBigGeom<N>::THREADS, N >= 16384 ? 1 : (N >= 8192 ? 2 : 4))
 fft_c2c_big_kernel(const cx<float> *__restrict__ in, cx<float> *__restrict__ out, long batch, const cx<float> *__restrict__ tw, float scale) {
     using Geo = FftBigGeom<N>;
     constexpr int E = Geo::E, G = Geo::G;

@@ -4,9 +4,10 @@ import torch, json
 from jeicyboodsp_b200.binding import Context, Library
 PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
 L = Library(); ctx = Context(L, 0, stream=torch.cuda.current_stream().cuda_stream)
-total = 1 << 28
+total = 1 << (int(sys.argv[1]) if len(sys.argv) > 1 else 28)
 x = torch.randn(total, dtype=torch.complex64, device="cuda"); y = torch.empty_like(x)
-for lg in range(8, 17):
+lo = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+for lg in range(lo, 17):
     n = 1 << lg
     for _ in range(3): ctx.fft_c2c_f32(x, y, n, total // n, True)
     ts = []
