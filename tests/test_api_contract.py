@@ -93,3 +93,43 @@ def test_empty_batches_are_no_ops(be):
     feat = be.zeros((1, 1, 13), np.float32)
     assert plan.run(be.zeros((1, 392), np.int16), 392, 1, 392, feat, 13) == 0
     plan.close()
+
+
+def test_pitch_contract(be, oracle):
+    """Pitch entry points: bad presets / framings / lag bounds are rejected, an empty call is a no-op, a padded row pitch
+    and a state reset behave, and the host form applies the stale-tail rule to a short final block."""
+    with pytest.raises(JdspError):
+        be.L.pitch_params("nope")
+    p = be.L.pitch_params("ref")
+    assert (p.n_fft, p.block, p.min_lag, p.fs) == (1024, 512, 100, 16000.0)
+    bad = be.L.pitch_params("ref"); bad.n_fft = 2048
+    with pytest.raises(JdspError) as e:
+        be.ctx.pitch_state(bad, 1)
+    assert e.value.code == -4                                  # JDSP_ERR_UNSUPPORTED framing
+    bad = be.L.pitch_params("ref"); bad.min_lag = 511
+    with pytest.raises(JdspError):
+        be.ctx.pitch_state(bad, 1)
+    with pytest.raises(JdspError):
+        be.ctx.pitch_state(p, 0)
+    H, nb, S, pad = p.block, 6, 3, 24
+    x = np.stack([synth.denoise_stream(90 + s, nb * H) for s in range(S)])
+    xp = np.zeros((S, nb * H + pad), np.int16); xp[:, : nb * H] = x
+    st = be.ctx.pitch_state(p, S)
+    arg = be.zeros((S, nb), np.int32)
+    st.run(be.to_dev(xp), nb * H + pad, 0, arg, None)          # zero blocks: nothing happens, the keep buffer stays zero
+    st.run(be.to_dev(xp), nb * H + pad, nb, arg, None)         # padded rows
+    first = be.to_host(arg).copy()
+    st.run(be.to_dev(xp), nb * H + pad, nb, arg, None)         # continues: block 0 now pairs with the previous call's last block
+    cont = be.to_host(arg).copy()
+    st.reset()
+    st.run(be.to_dev(xp), nb * H + pad, nb, arg, None)
+    again = be.to_host(arg).copy()
+    st.close()
+    for s in range(S):
+        assert np.array_equal(first[s], oracle.pitch(x[s], exact=True)[0])
+        assert np.array_equal(cont[s], oracle.pitch(np.concatenate([x[s], x[s]]), exact=True)[0][nb:])
+    assert np.array_equal(first, again)
+    short = x[0][: 3 * H + 77]                                  # host form, short final block keeps the previous block's tail
+    a, r = be.ctx.pitch(short, p)
+    ea, er = oracle.pitch(short, exact=True)
+    assert a.shape == (1, 4) and np.array_equal(a[0], ea) and np.array_equal(r[0], er)

@@ -68,6 +68,24 @@ def test_fft_c2c_f32_persistent_loops(be, n):
     assert np.abs(back / n - z).max() <= 1e-5
 
 
+@pytest.mark.parametrize("plan,sizes", [("JDSP_FFT_NO_BIG", (4096, 8192, 16384)),       # TMA-prefetched kernel / four-step instead of on-chip
+                                        ("JDSP_FFT_NO_BIG,JDSP_FFT_NO_PIPE", (2048, 4096, 8192)),   # the plain on-chip kernel
+                                        ("JDSP_FFT_NO_BIG,JDSP_FFT_FUSED", (16384, 32768, 65536))])  # one persistent four-step kernel
+def test_fft_alternate_plans(be, monkeypatch, plan, sizes):
+    """The measured-and-kept-as-fallback FFT plans stay correct (they are selected by environment variables only)."""
+    for v in plan.split(","):
+        monkeypatch.setenv(v, "1")
+    for n in sizes:
+        batch = 40 if be.name == "gpu" else 3
+        rng = np.random.default_rng(n + 7)
+        z = (rng.uniform(-1, 1, (batch, n)) + 1j * rng.uniform(-1, 1, (batch, n))).astype(np.complex64)
+        d_out = be.zeros((batch, n), np.complex64)
+        for fwd in (True, False):
+            be.ctx.fft_c2c_f32(be.to_dev(z), d_out, n, batch, fwd)
+            ref = np.fft.fft(z.astype(np.complex128), axis=1) if fwd else np.fft.ifft(z.astype(np.complex128), axis=1) * n
+            assert np.abs(be.to_host(d_out) - ref).max() <= 1e-4 * np.abs(ref).max(), (plan, n, fwd)
+
+
 @pytest.mark.parametrize("n", [2, 64, 512, 1024, 8192, 16384, 65536])
 def test_fft_process_host_dropin_f64(be, oracle, n):
     rng = np.random.default_rng(n)
