@@ -392,6 +392,14 @@ JDSP_DEV void mbar_wait(uint64_t *bar, unsigned parity) {
 #endif
 }
 
+// (q, r) = divmod(i, d) kept up to date while i advances by a fixed stride: one 64-bit division per thread instead of one
+// per loop iteration (a 64-bit divide is ~40 instructions; the persistent tile loops below ran two or three per tile).
+struct StridedDivmod {
+    long q, r, dq, dr, d;
+    JDSP_DEV StridedDivmod(long i0, long stride, long d_) : d(d_) { q = i0 / d_; r = i0 % d_; dq = stride / d_; dr = stride % d_; }
+    JDSP_DEV void next() { q += dq; r += dr; if (r >= d) { r -= d; ++q; } }
+};
+
 // ---- small numeric helpers ---------------------------------------------------------------------------
 // (short)(double) of the reference: truncate toward zero, keep the low 16 bits
 JDSP_DEV int16_t trunc16(float v) { return (int16_t)__float2int_rz(v); }

@@ -262,26 +262,27 @@ __global__ void __launch_bounds__(MfccGeom<NC>::NT) mfcc_kernel(MfccArgs a) {
     const long tiles_per_utt = (n_frames + F - 1) / F;
     const long n_tiles = a.n_utts * tiles_per_utt;
     // bytes of PCM a tile needs: (nf-1)*hop + frame_len samples (hop and frame_len are multiples of 8 samples)
-    auto issue = [&](long tile, int bufi) {
-        const long u = tile / tiles_per_utt, t0 = (tile % tiles_per_utt) * F;
+    auto issue = [&](long u, long t0, int bufi) {
         const int nf = (n_frames - t0 < F) ? (int)(n_frames - t0) : F;
         const unsigned bytes = (unsigned)(((nf - 1) * hop + W) * 2);
         mbar_expect_tx(&bars[bufi], bytes);
         bulk_g2s(reinterpret_cast<unsigned char *>(xsb) + bufi * span_b, a.in + u * in_pitch + t0 * hop, bytes, &bars[bufi]);
     };
     __syncthreads();
-    if (tid == 0 && (long)blockIdx.x < n_tiles) issue(blockIdx.x, 0);
+    StridedDivmod dm(blockIdx.x, gridDim.x, tiles_per_utt);   // (utterance, tile within it) of the current tile
+    if (tid == 0 && (long)blockIdx.x < n_tiles) issue(dm.q, dm.r * F, 0);
     unsigned phase0 = 0, phase1 = 0;
     int cur = 0;
 
     for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long u = tile / tiles_per_utt;
-        const long t0 = (tile % tiles_per_utt) * F;
+        const long u = dm.q;
+        const long t0 = dm.r * F;
+        dm.next();
         const int nf = (n_frames - t0 < F) ? (int)(n_frames - t0) : F;
         const int16_t *xs = reinterpret_cast<const int16_t *>(reinterpret_cast<unsigned char *>(xsb) + cur * span_b);
         if (cur == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1u; } else { mbar_wait(&bars[1], phase1); phase1 ^= 1u; }
         __syncthreads();  // (A) PCM landed; previous tile finished with fbuf / mag / mel
-        if (tid == 0 && tile + gridDim.x < n_tiles) issue(tile + gridDim.x, cur ^ 1);
+        if (tid == 0 && tile + gridDim.x < n_tiles) issue(dm.q, dm.r * F, cur ^ 1);
         // ---- pre-emphasis (:208-210), window (:212-214), packed real transform of frame g ------------
         cf reg[E];
         cf *buf = fbuf + g * FP;

@@ -225,14 +225,14 @@ fft_cols_kernel(const cx<T> *__restrict__ in, cx<T> *__restrict__ tmp, int N2, l
     static_assert(PER == E && THREADS % CT == 0, "staging assumes one element per (row-slab, column)");
     JDSP_DYN_SMEM(smem_raw);
     cx<T> *sm = reinterpret_cast<cx<T> *>(smem_raw);
-    const int tiles_per_fft = N2 / CT;
+    const int tiles_per_fft = N2 / CT, tshift = __ffs(tiles_per_fft) - 1;
     const long n_tiles = n_fft * tiles_per_fft;
     const long N = (long)N1 * N2;
     const int sc = threadIdx.x % CT, sr = threadIdx.x / CT;   // staging role: column sc, rows sr + (THREADS/CT)*i
     const int c = threadIdx.x / G, t = threadIdx.x % G;       // transform role: column c, lane t
     for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long f = tile / tiles_per_fft;
-        const int c0 = (int)(tile % tiles_per_fft) * CT;
+        const long f = tile >> tshift;                          // tiles per transform is a power of two
+        const int c0 = (int)(tile & (tiles_per_fft - 1)) * CT;
         const cx<T> *src = in + f * N + c0 + sc;
         cx<T> *dst = tmp + f * N + c0 + sc;
         cx<T> st[PER];
@@ -245,7 +245,7 @@ fft_cols_kernel(const cx<T> *__restrict__ in, cx<T> *__restrict__ tmp, int N2, l
             const long nt = tile + gridDim.x;
             if (nt < n_tiles) {
                 constexpr int LPR = (CT * (int)sizeof(cx<T>) + 127) / 128;
-                const cx<T> *nsrc = in + (nt / tiles_per_fft) * N + (int)(nt % tiles_per_fft) * CT;
+                const cx<T> *nsrc = in + (nt >> tshift) * N + (int)(nt & (tiles_per_fft - 1)) * CT;
                 for (int i = threadIdx.x; i < N1 * LPR; i += THREADS)
                     prefetch_l2(reinterpret_cast<const char *>(nsrc + (long)(i / LPR) * N2) + (i % LPR) * 128);
             }
@@ -258,7 +258,12 @@ fft_cols_kernel(const cx<T> *__restrict__ in, cx<T> *__restrict__ tmp, int N2, l
         cx<T> *buf = sm + c * PADN;
         fft_load_regs<T, N1, E>(reg, t, buf);
         group_sync<0>();
-        group_fft<T, N1, E, INV, 0>(reg, t, buf, tw1);
+        const cx<T> *tw1p = tw1;
+#ifndef JDSP_EMUL
+        // keep the read-only twiddle loads of the passes below the staging loads (ptxas hoists them otherwise: 100 bytes of spills at 80 registers)
+        asm volatile("" : "+l"(tw1p)::"memory");
+#endif
+        group_fft<T, N1, E, INV, 0>(reg, t, buf, tw1p);
         group_sync<0>();
         {
             const cx<T> b2 = cmul<false>(b1, b1), b3 = cmul<false>(b2, b1);
@@ -296,14 +301,14 @@ fft_rows_kernel(const cx<T> *__restrict__ tmp, cx<T> *__restrict__ out, int N1, 
     static_assert(G <= 32 && G >= 16, "row transforms must fit a warp-level group of at least 16 lanes");
     JDSP_DYN_SMEM(smem_raw);
     cx<T> *sm = reinterpret_cast<cx<T> *>(smem_raw);
-    const int tiles_per_fft = N1 / RT;
+    const int tiles_per_fft = N1 / RT, tshift = __ffs(tiles_per_fft) - 1;
     const long n_tiles = n_fft * tiles_per_fft;
     const long N = (long)N1 * N2;
     const int r = threadIdx.x / G, t = threadIdx.x % G;       // transform role
     const int orr = threadIdx.x % RT, ok = threadIdx.x / RT;  // output role: row orr, k2 = ok + (THREADS/RT)*i
     for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long f = tile / tiles_per_fft;
-        const int r0 = (int)(tile % tiles_per_fft) * RT;
+        const long f = tile >> tshift;
+        const int r0 = (int)(tile & (tiles_per_fft - 1)) * RT;
         const cx<T> *src = tmp + f * N + (long)(r0 + r) * N2 + t;
         cx<T> *dst = out + f * N + r0 + orr;
         cx<T> reg[E];
@@ -313,7 +318,7 @@ fft_rows_kernel(const cx<T> *__restrict__ tmp, cx<T> *__restrict__ out, int N1, 
         {   // next tile of this CTA -> L2 (RT adjacent rows are one contiguous run)
             const long nt = tile + gridDim.x;
             if (nt < n_tiles) {
-                const char *nsrc = reinterpret_cast<const char *>(tmp + (nt / tiles_per_fft) * N + (long)((int)(nt % tiles_per_fft) * RT) * N2);
+                const char *nsrc = reinterpret_cast<const char *>(tmp + (nt >> tshift) * N + (long)((int)(nt & (tiles_per_fft - 1)) * RT) * N2);
                 for (int i = threadIdx.x; i < (int)(RT * N2 * sizeof(cx<T>) / 128); i += THREADS) prefetch_l2(nsrc + (long)i * 128);
             }
         }

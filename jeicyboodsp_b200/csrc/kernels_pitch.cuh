@@ -74,8 +74,9 @@ __global__ void __launch_bounds__(PitchGeom<NC>::NT) pitch_kernel(PitchArgs a) {
     const long n_items = a.n_streams * a.n_blocks;
     const int min_lag = a.min_lag;
 
-    for (long item = (long)blockIdx.x * Geo::WARPS + w; item < n_items; item += (long)gridDim.x * Geo::WARPS) {
-        const long s = item / a.n_blocks, b = item % a.n_blocks;
+    StridedDivmod dm((long)blockIdx.x * Geo::WARPS + w, (long)gridDim.x * Geo::WARPS, a.n_blocks);
+    for (long item = (long)blockIdx.x * Geo::WARPS + w; item < n_items; item += (long)gridDim.x * Geo::WARPS, dm.next()) {
+        const long s = dm.q, b = dm.r;
         const uint32_t *cur = reinterpret_cast<const uint32_t *>(a.in + s * a.in_pitch + b * H);
         const uint32_t *prv = b > 0 ? reinterpret_cast<const uint32_t *>(a.in + s * a.in_pitch + (b - 1) * H)
                                     : reinterpret_cast<const uint32_t *>(a.st_prev + s * H);

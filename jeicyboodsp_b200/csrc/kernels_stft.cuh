@@ -83,9 +83,10 @@ __global__ void __launch_bounds__(RoundtripGeom<N>::THREADS) roundtrip_kernel(Ro
     const long n_tiles = a.n_streams * tiles_per_stream;
     const int grp = threadIdx.x / G, t = threadIdx.x % G;
     const float inv_n = 1.0f / (float)N;
-    for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long s = tile / tiles_per_stream;
-        const long pair0 = (tile % tiles_per_stream) * FPB;
+    StridedDivmod dm(blockIdx.x, gridDim.x, tiles_per_stream);
+    for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, dm.next()) {
+        const long s = dm.q;
+        const long pair0 = dm.r * FPB;
         const long samp0 = pair0 * 2 * N;                                   // first sample of the tile in its row
         long valid = a.n_blocks * (long)N - samp0;                          // samples available from samp0
         if (valid > (long)FPB * 2 * N) valid = (long)FPB * 2 * N;

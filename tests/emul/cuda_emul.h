@@ -149,6 +149,7 @@ template <typename T> static inline T __ldg(const T *p) { return *p; }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int __clz(unsigned x) { return x ? __builtin_clz(x) : 32; }
 static inline unsigned __brev(unsigned x) {
     unsigned r = 0;
