@@ -214,7 +214,7 @@ fft_c2c_big_kernel(const cx<float> *__restrict__ in, cx<float> *__restrict__ out
 // Global accesses are CT*sizeof(cx) contiguous bytes per row; all loads of a tile are issued before the first
 // shared-memory store so a CTA keeps its whole tile in flight.
 template <typename T, int N1, int CT, bool INV>
-__global__ void __launch_bounds__(CT * FftGeom<N1>::G, sizeof(T) == 4 ? (CT * FftGeom<N1>::G >= 512 ? 2 : 768 / (CT * FftGeom<N1>::G)) : 1)
+__global__ void __launch_bounds__(CT * FftGeom<N1>::G, sizeof(T) == 4 ? (CT * FftGeom<N1>::G >= 512 ? 2 : 512 / (CT * FftGeom<N1>::G)) : 1)
 fft_cols_kernel(const cx<T> *__restrict__ in, cx<T> *__restrict__ tmp, int N2, long n_fft, const cx<T> *__restrict__ tw1,
                 const cx<T> *__restrict__ twN) {
     using Geo = FftGeom<N1>;
