@@ -59,11 +59,13 @@ def want(name):
 # ---- config 5: batched c2c size sweep, 2^29 points (4 GiB in + 4 GiB out) -----------------------------------------
 if want("sweep"):
     total = (1 << 29) if not args.quick else (1 << 26)
-    x = torch.empty(total, dtype=torch.complex64, device=dev)
+    # one allocation, input in the first half and output in the second: the distance between the two streams is then
+    # exactly the buffer size (measured: other placements cost the N >= 4096 kernels 3-8 %, tools/_probe_offset.py)
+    xy = torch.empty(2 * total, dtype=torch.complex64, device=dev)
+    x, y = xy[:total], xy[total:]
     xr = torch.view_as_real(x)
     g = torch.Generator(device=dev); g.manual_seed(5)
     xr.uniform_(-1, 1, generator=g)
-    y = torch.empty_like(x)
     for lg in range(8, 17):
         n = 1 << lg
         batch = total // n
@@ -86,7 +88,7 @@ if want("sweep"):
             worst = max(worst, float(np.abs(got - ref).max() / np.abs(ref).max()))
         row["parity_max_rel"] = worst
         emit(row)
-    del x, y, xr
+    del x, y, xr, xy
     torch.cuda.empty_cache()
 
 # ---- config 1: FFT -> IFFT round trip ------------------------------------------------------------------------------
