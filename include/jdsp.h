@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define JDSP_ABI_VERSION 2
+#define JDSP_ABI_VERSION 3
 
 #define JDSP_OK 0
 #define JDSP_ERR_INVALID (-1)     /* bad argument */
@@ -165,6 +165,45 @@ int jdsp_pitch_i16_dev(jdsp_ctx *ctx, jdsp_pitch_state *st, const int16_t *d_in,
  * short final block (:60-64); arg / rmax rows hold ceil(n/block) entries, returned in *n_blocks (nullable). */
 int jdsp_pitch_i16(jdsp_ctx *ctx, const jdsp_pitch_params *p, const int16_t *in, long in_pitch, long n_streams, long n_samples,
                    int32_t *arg, double *rmax, long *n_blocks);
+
+/* ---- B1: two-microphone MVDR beamformer (BeamForming_MVDR_ver1.cpp:84-269) --------------------- */
+typedef struct {
+    int32_t n_fft;     /* FFT_PROCESSING_LEN (:34): 1024                                                          */
+    int32_t block;     /* BLOCK_LEN (:35): 512                                                                    */
+    int32_t keep;      /* KEEP_LEN (:36): 511.  frame = [first keep samples of the previous block | block | 0]   */
+    int32_t reserved;
+    double energy_thr; /* THRESHOLD_OF_ENERGY (:31): 700; the zero-crossing count is printed, never tested (:235) */
+    double fs;         /* SAMPLING_RATE (:33): 16000                                                              */
+    double dtime;      /* dTime = (DISTANCE_OF_MIC / SPEED_OF_SOUND) * sin(angle) (:60): 0 in the program         */
+    double win_a0, win_a1; /* VAD Hamming window 0.54 / 0.46 (:224)                                               */
+    double pi_literal;     /* 3.141592 (:38)                                                                      */
+} jdsp_mvdr_params;
+int jdsp_mvdr_params_preset(const char *name /* "ref" */, jdsp_mvdr_params *p);
+/* Replaces main's locals and the callee's statics for every microphone pair: iNumOfIteration, rgsTempBufferL/R,
+ * rgdSpatialCorr (:53-57), ProcessMVDR's keep buffers and call counter (:123-126). */
+typedef struct jdsp_mvdr_state jdsp_mvdr_state;
+int jdsp_mvdr_state_create(jdsp_ctx *ctx, const jdsp_mvdr_params *p, long n_streams, jdsp_mvdr_state **st);
+int jdsp_mvdr_state_reset(jdsp_ctx *ctx, jdsp_mvdr_state *st);
+int jdsp_mvdr_state_destroy(jdsp_ctx *ctx, jdsp_mvdr_state *st);
+/*
+ * One call = main's loop body (:95-112) over `n_blocks` consecutive whole blocks of every microphone pair:
+ * VoiceActivityDetection on the left block, EstimateSpatialCorrMtx on runs of non-voice blocks, ProcessMVDR.
+ *   d_left, d_right [stream][n_blocks*block], row pitch in_pitch (even).
+ *   d_out  [stream][emitted*block] int16; the very first block of a stream emits nothing (:202-205), so
+ *          emitted = n_blocks - 1 on a fresh state, n_blocks afterwards; returned in *n_out_blocks (nullable).
+ *          Blocks processed while the spatial matrix is still singular are zeros (the program's NaN -> (short) 0).
+ *   d_out_f32 (nullable) the same samples before the (short) cast.   d_vad (nullable) [stream][n_blocks] 0/1.
+ */
+int jdsp_mvdr_i16_dev(jdsp_ctx *ctx, jdsp_mvdr_state *st, const int16_t *d_left, const int16_t *d_right, long in_pitch,
+                      long n_blocks, int16_t *d_out, long out_pitch, float *d_out_f32, long f32_pitch, uint8_t *d_vad,
+                      long *n_out_blocks);
+/* rgdSpatialCorr[0][0], [1][1] per stream (host doubles [n_streams][2]); the off-diagonal sums cancel exactly for real
+ * input (the program holds rounding noise there). */
+int jdsp_mvdr_spatial_corr(jdsp_ctx *ctx, jdsp_mvdr_state *st, double *corr);
+/* Host form: n_streams microphone pairs of n_samples each (PCM after the 44-byte headers, :81-82); stale-tail rule on a
+ * short final block; out rows hold (ceil(n/block) - 1) * block samples, returned in *n_out_samples (nullable). */
+int jdsp_mvdr_i16(jdsp_ctx *ctx, const jdsp_mvdr_params *p, const int16_t *left, const int16_t *right, long in_pitch,
+                  long n_streams, long n_samples, int16_t *out, long out_pitch, long *n_out_samples);
 
 /* ---- C1: FFT overlap-save convolution (AnalySisFreqDomain, Fast_Convolution_Based_3DAudio_Impl.cpp:102-177) */
 typedef struct {

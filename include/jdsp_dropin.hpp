@@ -166,5 +166,43 @@ class PitchStream {
     double *d_max_ = nullptr;
 };
 
+// bool ProcessMVDR(short *L, short *R, int iBlockLen, short *out, double dTime, double (*rgdSpatialCorr)[CHANNEL]) together with
+// the VAD / EstimateSpatialCorrMtx calls main makes before it (BeamForming_MVDR_ver1.cpp:42-44,95-112): one microphone pair,
+// one block per call; main's locals and the callee's statics live in the state.  Returns true when a block was emitted.
+class MvdrStream {
+  public:
+    explicit MvdrStream(const char *preset = "ref", double dTime = 0.0) {
+        check(jdsp_mvdr_params_preset(preset, &p_), "mvdr preset");
+        p_.dtime = dTime;
+        check(jdsp_mvdr_state_create(default_ctx(), &p_, 1, &st_), "mvdr state");
+        check(jdsp_malloc(default_ctx(), (void **)&d_l_, p_.block * sizeof(int16_t)), "malloc");
+        check(jdsp_malloc(default_ctx(), (void **)&d_r_, p_.block * sizeof(int16_t)), "malloc");
+        check(jdsp_malloc(default_ctx(), (void **)&d_out_, p_.block * sizeof(int16_t)), "malloc");
+    }
+    ~MvdrStream() {
+        jdsp_mvdr_state_destroy(default_ctx(), st_);
+        jdsp_free(default_ctx(), d_l_);
+        jdsp_free(default_ctx(), d_r_);
+        jdsp_free(default_ctx(), d_out_);
+    }
+    bool ProcessMVDR(const short *rgsInputBufferL, const short *rgsInputBufferR, int iBlockLen, short *rgsOutputBuffer) {
+        if (iBlockLen != p_.block) throw std::invalid_argument("iBlockLen must equal BLOCK_LEN");
+        jdsp_ctx *c = default_ctx();
+        long emitted = 0;
+        check(jdsp_memcpy_h2d(c, d_l_, rgsInputBufferL, p_.block * sizeof(int16_t)), "h2d");
+        check(jdsp_memcpy_h2d(c, d_r_, rgsInputBufferR, p_.block * sizeof(int16_t)), "h2d");
+        check(jdsp_mvdr_i16_dev(c, st_, d_l_, d_r_, p_.block, 1, d_out_, p_.block, nullptr, 0, nullptr, &emitted), "mvdr");
+        if (emitted) check(jdsp_memcpy_d2h(c, rgsOutputBuffer, d_out_, p_.block * sizeof(int16_t)), "d2h");
+        check(jdsp_sync(c), "sync");
+        return emitted == 1;
+    }
+    const jdsp_mvdr_params &params() const { return p_; }
+
+  private:
+    jdsp_mvdr_params p_;
+    jdsp_mvdr_state *st_ = nullptr;
+    int16_t *d_l_ = nullptr, *d_r_ = nullptr, *d_out_ = nullptr;
+};
+
 }  // namespace jdsp
 #endif

@@ -49,6 +49,12 @@ class PitchParams(C.Structure):
                 ("fs", C.c_double)]
 
 
+class MvdrParams(C.Structure):
+    _fields_ = [("n_fft", C.c_int32), ("block", C.c_int32), ("keep", C.c_int32), ("reserved", C.c_int32),
+                ("energy_thr", C.c_double), ("fs", C.c_double), ("dtime", C.c_double), ("win_a0", C.c_double),
+                ("win_a1", C.c_double), ("pi_literal", C.c_double)]
+
+
 def _ptr(x):
     """Raw address of a numpy array / torch tensor / int / None."""
     if x is None:
@@ -77,6 +83,8 @@ ABI_SYMBOLS = [
     "jdsp_mfcc_frames_i16_dev", "jdsp_mfcc_program_i16",
     "jdsp_pitch_params_preset", "jdsp_pitch_state_create", "jdsp_pitch_state_reset", "jdsp_pitch_state_destroy",
     "jdsp_pitch_i16_dev", "jdsp_pitch_i16",
+    "jdsp_mvdr_params_preset", "jdsp_mvdr_state_create", "jdsp_mvdr_state_reset", "jdsp_mvdr_state_destroy",
+    "jdsp_mvdr_i16_dev", "jdsp_mvdr_spatial_corr", "jdsp_mvdr_i16",
 ]
 
 
@@ -123,6 +131,11 @@ class Library:
     def pitch_params(self, preset: str = "ref") -> PitchParams:
         p = PitchParams()
         self.check(self.lib.jdsp_pitch_params_preset(preset.encode(), C.byref(p)))
+        return p
+
+    def mvdr_params(self, preset: str = "ref") -> MvdrParams:
+        p = MvdrParams()
+        self.check(self.lib.jdsp_mvdr_params_preset(preset.encode(), C.byref(p)))
         return p
 
 
@@ -235,6 +248,25 @@ class Context:
         assert got.value == nb
         return arg[:, :nb], rmax[:, :nb]
 
+    # ---- MVDR beamformer (BeamForming_MVDR_ver1) ---------------------------------------------------------------
+    def mvdr_state(self, params: MvdrParams, n_streams: int) -> "MvdrState":
+        return MvdrState(self, params, n_streams)
+
+    def mvdr(self, left: np.ndarray, right: np.ndarray, params: MvdrParams) -> np.ndarray:
+        """Host form: int16 [n_streams, n_samples] per microphone -> int16 [n_streams, (ceil(n/block)-1)*block]."""
+        left = np.ascontiguousarray(np.atleast_2d(left), np.int16)
+        right = np.ascontiguousarray(np.atleast_2d(right), np.int16)
+        assert left.shape == right.shape
+        S, n = left.shape
+        nb = -(-n // params.block)
+        n_out = max(nb - 1, 0) * params.block
+        out = np.zeros((S, max(n_out, 1)), np.int16)
+        got = C.c_long(0)
+        self.L.check(self.lib.jdsp_mvdr_i16(self.h, C.byref(params), _ptr(left), _ptr(right), C.c_long(left.shape[1]), C.c_long(S),
+                                            C.c_long(n), _ptr(out), C.c_long(out.shape[1]), C.byref(got)))
+        assert got.value == n_out
+        return out[:, :n_out]
+
     # ---- fast convolution ---------------------------------------------------------------------------------
     def fastconv_state(self, params: FastconvParams, n_sources: int, taps: np.ndarray) -> "FastconvState":
         return FastconvState(self, params, n_sources, taps)
@@ -287,6 +319,35 @@ class PitchState:
         """Device form: d_in int16 [n_streams, in_pitch]; d_arg int32 [n_streams, n_blocks]; d_rmax float64 or None."""
         self.ctx.L.check(self.ctx.lib.jdsp_pitch_i16_dev(self.ctx.h, self.h, _ptr(d_in), C.c_long(in_pitch), C.c_long(n_blocks),
                                                          _ptr(d_arg), _ptr(d_rmax)))
+
+
+class MvdrState:
+    def __init__(self, ctx: Context, params: MvdrParams, n_streams: int):
+        self.ctx, self.params, self.n_streams = ctx, params, n_streams
+        self.h = C.c_void_p(0)
+        ctx.L.check(ctx.lib.jdsp_mvdr_state_create(ctx.h, C.byref(params), C.c_long(n_streams), C.byref(self.h)))
+
+    def reset(self) -> None:
+        self.ctx.L.check(self.ctx.lib.jdsp_mvdr_state_reset(self.ctx.h, self.h))
+
+    def close(self) -> None:
+        if self.h:
+            self.ctx.lib.jdsp_mvdr_state_destroy(self.ctx.h, self.h)
+            self.h = C.c_void_p(0)
+
+    def run(self, d_left, d_right, in_pitch: int, n_blocks: int, d_out, out_pitch: int, d_out_f32=None, f32_pitch: int = 0,
+            d_vad=None) -> int:
+        """Device form; returns the number of blocks emitted per stream."""
+        got = C.c_long(0)
+        self.ctx.L.check(self.ctx.lib.jdsp_mvdr_i16_dev(self.ctx.h, self.h, _ptr(d_left), _ptr(d_right), C.c_long(in_pitch),
+                                                        C.c_long(n_blocks), _ptr(d_out), C.c_long(out_pitch), _ptr(d_out_f32),
+                                                        C.c_long(f32_pitch), _ptr(d_vad), C.byref(got)))
+        return got.value
+
+    def spatial_corr(self) -> np.ndarray:
+        corr = np.zeros((self.n_streams, 2), np.float64)
+        self.ctx.L.check(self.ctx.lib.jdsp_mvdr_spatial_corr(self.ctx.h, self.h, _ptr(corr)))
+        return corr
 
 
 class DenoiseState:

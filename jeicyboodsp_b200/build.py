@@ -11,11 +11,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libjdsp.so")
-SOURCES = ["jdsp_api.cu", "jdsp_stft.cu", "jdsp_conv_mfcc.cu", "jdsp_pitch.cu"]
+SOURCES = ["jdsp_api.cu", "jdsp_stft.cu", "jdsp_conv_mfcc.cu", "jdsp_pitch.cu", "jdsp_mvdr.cu"]
 COMMON = ["jdsp_host.hpp", "jdsp_device.cuh", "../../include/jdsp.h"]
 DEPS = {"jdsp_api.cu": ["kernels_fft.cuh"], "jdsp_stft.cu": ["kernels_stft.cuh", "kernels_stream.cuh"],
         "jdsp_conv_mfcc.cu": ["kernels_conv_mfcc.cuh", "kernels_stft.cuh"],
-        "jdsp_pitch.cu": ["kernels_pitch.cuh", "kernels_stft.cuh"]}
+        "jdsp_pitch.cu": ["kernels_pitch.cuh", "kernels_stft.cuh"],
+        "jdsp_mvdr.cu": ["kernels_mvdr.cuh", "kernels_stft.cuh"]}
 HEADERS = COMMON + sorted({h for v in DEPS.values() for h in v})
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

@@ -1,0 +1,179 @@
+// kernels_mvdr.cuh -- two-microphone MVDR beamformer (BeamForming_MVDR_ver1.cpp:84-269).
+//
+// The program's state is tiny and its heavy part is frame-parallel, so the work splits three ways:
+//   mvdr_stats_kernel  one warp per (stream, block): the VAD decision on the left block (:209-243, bit-exact: Hamming
+//                      window product truncated to short in fp64, integer energy) and the exact energies sum l^2, sum r^2
+//                      of the block.  EstimateSpatialCorrMtx (:245-269) sums |L_i|^2 / N over ALL bins of the 1024-sample
+//                      buffer [previous non-voice block | block], which is the buffer's time-domain energy (Parseval), and
+//                      the cross terms -Lr Ri + Li Rr, which cancel exactly for real signals (the program's own values there
+//                      are FFT rounding noise, ~1e-10 against 1e7): so the 2x2 matrix is diag(EL, ER) from integer sums.
+//   mvdr_scan_kernel   one thread per stream walks the blocks (:95-108): run length of non-voice blocks, matrix updates from
+//                      the second block of a run on, the matrix in force for each block.
+//   mvdr_apply_kernel  one warp per (stream, block), ProcessMVDR (:121-207): frames [first 511 samples of the previous block |
+//                      block | 0] of both microphones ride ONE complex 1024-point transform (left in the real lane, right in
+//                      the imaginary lane; 32 points per thread, one shared-memory exchange); per bin the closed form of
+//                      w = R^-1 c / (c^H R^-1 c) for a diagonal R and c = (1, e^{j theta_i}):  w0 = ER / (EL + ER),
+//                      w1 = EL e^{j theta_i} / (EL + ER);  Y_i = conj(w0) L_i + conj(w1) R_i with the program's in-place product
+//                      (the imaginary part is formed from the already updated real part, :162-165); inverse transform, real
+//                      part / N of samples [511, 1023), (short).  A singular matrix (no estimate yet, or a silent microphone)
+//                      makes the program emit NaN -> (short) 0: zeros here.
+#pragma once
+#include "kernels_stft.cuh"
+
+namespace jdsp {
+
+struct MvdrArgs {
+    const int16_t *l, *r; long in_pitch; long n_blocks;
+    int16_t *out; long out_pitch;
+    float *out_f32; long f32_pitch;
+    const double *win_vad;         // [B]   w[511 + i]
+    const cf *tw;                  // pass twiddles for length 1024, 32 points per thread
+    const float2 *steer;           // [N]   (cos, sin) theta_i
+    // per-stream state
+    const int16_t *st_prev_l, *st_prev_r;   // [stream][B] previous block (zeros before the first)
+    int32_t *st_iter;              // run length of non-voice blocks
+    long long *st_pl, *st_pr;      // energies of the last non-voice block (first half of the program's temp buffers)
+    double *st_el, *st_er;         // the matrix diag(EL, ER)
+    // per-call scratch
+    uint8_t *voice; long long *sl2, *sr2;   // [stream][n_blocks]
+    double *el, *er;                         // [stream][n_blocks] matrix in force for each block
+    uint8_t *vad_out;                        // nullable [stream][n_blocks]
+    long n_streams;
+    double energy_thr;
+    long skip_blocks;              // 1 when the state has seen no block yet (:202-205)
+};
+
+struct MvdrGeom {
+    static constexpr int N = 1024, B = 512, K = 511, E = 32, G = N / E, WARPS = 4, NT = WARPS * 32;
+    static constexpr int PADN = padded_len_e<E>(N);
+    static constexpr size_t SMEM = (size_t)WARPS * PADN * sizeof(cf);
+    static_assert(G == 32, "one warp per frame pair");
+};
+
+JDSP_DEV long long warp_sum_i64(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(128) mvdr_stats_kernel(MvdrArgs a) {
+    constexpr int B = MvdrGeom::B, N = MvdrGeom::N;
+    const int w = threadIdx.x / 32, t = threadIdx.x % 32;
+    const long n_items = a.n_streams * a.n_blocks;
+    StridedDivmod dm((long)blockIdx.x * 4 + w, (long)gridDim.x * 4, a.n_blocks);
+    for (long item = (long)blockIdx.x * 4 + w; item < n_items; item += (long)gridDim.x * 4, dm.next()) {
+        const long s = dm.q, b = dm.r;
+        const uint32_t *pl = reinterpret_cast<const uint32_t *>(a.l + s * a.in_pitch + b * B);
+        const uint32_t *pr = reinterpret_cast<const uint32_t *>(a.r + s * a.in_pitch + b * B);
+        const double2 *w2 = reinterpret_cast<const double2 *>(a.win_vad);
+        long long ev = 0, el = 0, er = 0;
+#pragma unroll
+        for (int q = 0; q < B / 2 / 32; ++q) {
+            const int wi = t + 32 * q;
+            const uint32_t wl = pl[wi], wr = pr[wi];
+            const int l0 = (int)(int16_t)(wl & 0xffffu), l1 = (int)wl >> 16, r0 = (int)(int16_t)(wr & 0xffffu), r1 = (int)wr >> 16;
+            const double2 ww = w2[wi];
+            const int v0 = __double2int_rz((double)l0 * ww.x), v1 = __double2int_rz((double)l1 * ww.y);   // short *= double (:224)
+            ev += (long long)v0 * v0 + (long long)v1 * v1;                                               // :228
+            el += (long long)l0 * l0 + (long long)l1 * l1;
+            er += (long long)r0 * r0 + (long long)r1 * r1;
+        }
+        ev = warp_sum_i64(ev); el = warp_sum_i64(el); er = warp_sum_i64(er);
+        if (t == 0) {
+            const int voice = ((double)ev / (double)N > a.energy_thr) ? 1 : 0;                           // :235-238
+            a.voice[item] = (uint8_t)voice;
+            a.sl2[item] = el; a.sr2[item] = er;
+            if (a.vad_out) a.vad_out[item] = (uint8_t)voice;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) mvdr_scan_kernel(MvdrArgs a) {
+    const long s = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.n_streams) return;
+    int iter = a.st_iter[s];
+    long long pl = a.st_pl[s], pr = a.st_pr[s];
+    double el = a.st_el[s], er = a.st_er[s];
+    for (long b = 0; b < a.n_blocks; ++b) {
+        const long i = s * a.n_blocks + b;
+        if (!a.voice[i]) {                                   // :95-105
+            ++iter;
+            if (iter > 1) { el += (double)(pl + a.sl2[i]); er += (double)(pr + a.sr2[i]); }
+            pl = a.sl2[i]; pr = a.sr2[i];
+        } else {
+            iter = 0;
+        }
+        a.el[i] = el; a.er[i] = er;
+    }
+    a.st_iter[s] = iter; a.st_pl[s] = pl; a.st_pr[s] = pr; a.st_el[s] = el; a.st_er[s] = er;
+}
+
+__global__ void __launch_bounds__(MvdrGeom::NT) mvdr_apply_kernel(MvdrArgs a) {
+    using Geo = MvdrGeom;
+    constexpr int N = Geo::N, B = Geo::B, K = Geo::K, E = Geo::E, G = Geo::G;
+    JDSP_DYN_SMEM(smem_raw);
+    const int w = threadIdx.x / 32, t = threadIdx.x % 32;
+    cf *buf = reinterpret_cast<cf *>(smem_raw) + w * Geo::PADN;
+    const long n_items = a.n_streams * a.n_blocks;
+    const float inv_n = 1.0f / (float)N;
+    StridedDivmod dm((long)blockIdx.x * Geo::WARPS + w, (long)gridDim.x * Geo::WARPS, a.n_blocks);
+    for (long item = (long)blockIdx.x * Geo::WARPS + w; item < n_items; item += (long)gridDim.x * Geo::WARPS, dm.next()) {
+        const long s = dm.q, b = dm.r;
+        const int16_t *cl = a.l + s * a.in_pitch + b * B, *cr = a.r + s * a.in_pitch + b * B;
+        const int16_t *pl = b > 0 ? cl - B : a.st_prev_l + s * B, *pr = b > 0 ? cr - B : a.st_prev_r + s * B;
+        // ---- z[n] = l[n] + j r[n] over the frame [previous block's first 511 | block | 0] (:136-141,193-194)
+        cf reg[E];
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+            const int n = t + G * m;
+            float xl = 0.f, xr = 0.f;
+            if (n < K) { xl = (float)pl[n]; xr = (float)pr[n]; }
+            else if (n < K + B) { xl = (float)cl[n - K]; xr = (float)cr[n - K]; }
+            reg[m] = cmake<float>(xl, xr);
+        }
+        __syncwarp();
+        group_fft<float, N, E, false, 0>(reg, t, buf, a.tw);
+        group_sync<0>();
+        fft_store_regs<float, N, E>(reg, t, buf);
+        group_sync<0>();
+        // ---- weights of this block (:144-152 in closed form for a diagonal matrix) ------------------------------------------
+        const double el = a.el[item], er = a.er[item];
+        const bool singular = !(el > 0.0) || !(er > 0.0);
+        const float w0 = singular ? 0.f : (float)(er / (el + er)), g1 = singular ? 0.f : (float)(el / (el + er));
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+            const int i = t + G * m;
+            const cf Z = reg[m], P = buf[padE<E>((N - i) & (N - 1))];     // Z_i and Z_{N-i}
+            // L_i = (Z_i + conj Z_{N-i}) / 2,  R_i = (Z_i - conj Z_{N-i}) / (2j)
+            const float lr = 0.5f * (Z.x + P.x), li = 0.5f * (Z.y - P.y);
+            const float rr = 0.5f * (Z.y + P.y), ri = -0.5f * (Z.x - P.x);
+            const float2 cs = a.steer[i];
+            // conj(w0) = (w0, -0);  conj(w1) = g1 (cos, -sin): the program keeps (real, -imag) and multiplies in place
+            const float lw0 = w0, lw1 = -0.f, rw0 = g1 * cs.x, rw1 = -(g1 * cs.y);
+            const float Lr = lr * lw0 - li * lw1;
+            const float Li = Lr * lw1 + li * lw0;           // :163 the already updated real part
+            const float Rr = rr * rw0 - ri * rw1;
+            const float Ri = Rr * rw1 + ri * rw0;           // :165
+            reg[m] = cmake<float>(Lr + Rr, Li + Ri);        // :166-167
+        }
+        group_sync<0>();   // all partner reads are done before the inverse transform reuses the buffer
+        group_fft<float, N, E, true, 0>(reg, t, buf, a.tw);
+        // ---- samples [511, 1023) of the real part / N, (short) (:189-191); the very first block of a stream emits nothing
+        const long ob = b - a.skip_blocks;
+        if (ob >= 0) {
+            int16_t *orow = a.out + s * a.out_pitch + ob * B;
+            float *frow = a.out_f32 ? a.out_f32 + s * a.f32_pitch + ob * B : nullptr;
+#pragma unroll
+            for (int m = 0; m < E; ++m) {
+                const int n = t + G * m;
+                if (n >= K && n < K + B) {
+                    const float v = singular ? 0.f : reg[m].x * inv_n;
+                    orow[n - K] = trunc16(v);
+                    if (frow) frow[n - K] = v;
+                }
+            }
+        }
+    }
+}
+
+}  // namespace jdsp

@@ -101,3 +101,14 @@ def hrir_pair(source: int, taps: int = 512, seed: int = 3) -> np.ndarray:
 def mfcc_utterance(utt: int, n: int = 160_000, fs: float = 16_000.0, seed: int = 4) -> np.ndarray:
     """Same speech family as config 2 but with noise sigma >= 5 everywhere (no digital silence -> no ln 0)."""
     return denoise_stream(utt, n, fs=fs, sigma=25.0, amp=6000.0, seed=seed)
+
+
+# ---- MVDR (SURVEY 8f rank 3): two-microphone recordings -----------------------------------------------------
+def mvdr_pair(stream: int, n: int, delay: int = 3, gain: float = 0.8, sigma_r: float = 35.0, seed: int = 6):
+    """Left microphone = a config-2 stream (speech gated off for 0.6 s of every 2 s, so runs of non-voice blocks feed the
+    spatial matrix); right microphone = the same scene `delay` samples later at `gain`, plus its own sensor noise."""
+    left = denoise_stream(stream, n)
+    rng = np.random.default_rng([seed, stream])
+    late = np.concatenate([np.zeros(delay), left[:n - delay].astype(np.float64)]) if delay else left.astype(np.float64)
+    right = gain * late + rng.normal(0, sigma_r, n)
+    return left, np.clip(np.round(right), -32768, 32767).astype(np.int16)

@@ -115,9 +115,15 @@ PT="$REF/PitchEstimation_method1.cpp"
 $CXX $OPT $W -I"$SHIM" -Dmain=ref_main -c "$PT" -o "$TMP/pitch_ref.o"
 $CXX "$TMP/pitch_ref.o" "$TMP/run_main.o" -o "$OUT/pitch_ref" -lm
 
+# ---- BeamForming_MVDR_ver1: needs Eigen (absent) -> oracle/eigen_shim serves MatrixXcd ---------------
+MV="$REF/BeamForming_MVDR_ver1.cpp"
+$CXX $OPT $W -I"$SHIM" -I"$HERE/eigen_shim" -Dmain=ref_main -c "$MV" -o "$TMP/mvdr_ref.o"
+$CXX "$TMP/mvdr_ref.o" "$TMP/run_main.o" -o "$OUT/mvdr_ref" -lm
+
 cat > "$OUT/README.txt" <<EOF
 Built by oracle/build.sh from the unmodified sources in $REF (g++ $($CXX -dumpversion), $OPT).
 FFT behind the FFTW call sites: oracle/fftw_shim/fftw3.h (radix-2, double, exact pi) - NOT FFTW.
+MatrixXcd behind BeamForming_MVDR_ver1: oracle/eigen_shim (Gauss-Jordan, partial pivoting) - NOT Eigen.
 Binaries only; git-ignored; travels to the GPU box with gpurun.
 EOF
 echo "[oracle] reference binaries -> $OUT"

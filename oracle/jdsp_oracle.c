@@ -23,6 +23,7 @@
  *   C-4  fast-conv warm-up blocks are pushed unfilled (Fast_Convolution...:119-123): DEFINED as zeros.
  *   C-1  (short) of a double: truncation toward zero then wrap modulo 2^16.
  */
+#include <complex.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -595,4 +596,119 @@ JO_API long jo_pitch_exact_i16(const int16_t *x, long n, int blk, int nfft, int 
     return nb;
 }
 
-JO_API int jo_abi_version(void) { return 2; }
+/* ================================================================================================
+ * MVDR: BeamForming_MVDR_ver1.cpp.  Two microphones, per block of 512 samples:
+ *   main (:84-112)  VAD on the LEFT block; a run of non-voice blocks feeds EstimateSpatialCorrMtx from its second block
+ *                   on with the 1024-sample buffers [previous non-voice block | block]; then ProcessMVDR on every block.
+ *   VAD (:209-243)  [511 zeros | block | 0] times a Hamming window, truncated to short IN PLACE, mean square > 700 = voice
+ *                   (the zero-crossing count is printed but not used; the keep buffer is never updated).
+ *   EstimateSpatialCorrMtx (:245-269)  R += (1/N) sum_i [ |L_i|^2, -Lr Ri + Li Rr ; -Rr Li + Ri Lr, |R_i|^2 ]  (a REAL 2x2
+ *                   matrix summed over all bins, never reset).
+ *   ProcessMVDR (:121-207)  frames [first 511 samples of the previous block | block | 0] (the keep copy at :193-194 starts at
+ *                   element KEEP_LEN, i.e. the block's first 511 samples), FFT both, steering c_i = (1, e^{j 2 pi i (fs/N) dTime}),
+ *                   w = R^-1 c / (c^H R^-1 c) (:151-152), Y_i = conj(w0) L_i + conj(w1) R_i with the program's in-place
+ *                   product (the imaginary part is formed from the ALREADY UPDATED real part, :162-165), IFFT, real part / N of
+ *                   samples [511, 1023), (short).  The first call emits nothing (:202-205).
+ * The program's angle is 0 (:58-60) so dTime = 0; dtime is a parameter here.  Eigen (absent from the reference tree) is
+ * restated as Gauss-Jordan elimination with partial pivoting on a 2x2 complex matrix, the arithmetic of oracle/eigen_shim.
+ * x86-64 gcc turns (short)NaN into 0 (cvttsd2si gives INT_MIN, low 16 bits 0): blocks before the first estimate are 0.
+ * ---------------------------------------------------------------------------------------------- */
+static void jo_inv2(double _Complex a[2][2], double _Complex inv[2][2]) {
+    inv[0][0] = 1.0; inv[0][1] = 0.0; inv[1][0] = 0.0; inv[1][1] = 1.0;
+    for (int col = 0; col < 2; ++col) {
+        int piv = col;
+        for (int i = col + 1; i < 2; ++i) if (cabs(a[i][col]) > cabs(a[piv][col])) piv = i;
+        for (int j = 0; j < 2; ++j) {
+            double _Complex t = a[col][j]; a[col][j] = a[piv][j]; a[piv][j] = t;
+            t = inv[col][j]; inv[col][j] = inv[piv][j]; inv[piv][j] = t;
+        }
+        const double _Complex p = a[col][col];
+        for (int j = 0; j < 2; ++j) { a[col][j] /= p; inv[col][j] /= p; }
+        for (int i = 0; i < 2; ++i) if (i != col) {
+            const double _Complex f = a[i][col];
+            for (int j = 0; j < 2; ++j) { a[i][j] -= f * a[col][j]; inv[i][j] -= f * inv[col][j]; }
+        }
+    }
+}
+static int16_t jo_short_of(double v) { return isnan(v) || fabs(v) >= 2147483648.0 ? (int16_t)0 : (int16_t)(int32_t)v; }
+
+JO_API long jo_mvdr_i16(const int16_t *xl, const int16_t *xr, long n, double dtime, int16_t *out, double *pre_out, double *corr_out,
+                        uint8_t *vad_out) {
+    enum { N = 1024, B = 512, K = 511 };
+    const double pi = 3.141592, fs = 16000.0;
+    int16_t bl[B] = {0}, br[B] = {0}, tl[2 * B] = {0}, tr[2 * B] = {0};
+    double keepl[K] = {0}, keepr[K] = {0};
+    double R[2][2] = {{0, 0}, {0, 0}};
+    double *a = (double *)calloc(2 * N, sizeof(double)), *b = (double *)calloc(2 * N, sizeof(double));
+    double *fl = (double *)calloc(2 * N, sizeof(double)), *fr = (double *)calloc(2 * N, sizeof(double));
+    long pos = 0, written = 0, calls = 0, nb = 0;
+    int iter = 0;
+    for (;;) {
+        if (jo_read_block(xl, n, pos, bl, B) <= 0) break;       /* :86-93 both files are read block by block */
+        if (jo_read_block(xr, n, pos, br, B) <= 0) break;
+        pos += B;
+        /* ---- VAD on the left block (:209-243) */
+        double energy = 0.0;
+        for (int i = 0; i < N; ++i) {
+            int16_t v = (i >= K && i < K + B) ? bl[i - K] : (int16_t)0;
+            v = (int16_t)(int32_t)((double)v * (0.54 - 0.46 * cos(2 * pi * i / (N - 1))));
+            energy += pow((double)v, 2.0);
+        }
+        energy /= N;
+        const int voice = energy > 700.0;
+        if (vad_out) vad_out[nb] = (uint8_t)voice;
+        if (!voice) {                                            /* :95-105 */
+            ++iter;
+            if (iter > 1) {
+                memcpy(tl + B, bl, sizeof(bl)); memcpy(tr + B, br, sizeof(br));
+                memset(a, 0, sizeof(double) * 2 * N); memset(b, 0, sizeof(double) * 2 * N);
+                for (int i = 0; i < 2 * B; ++i) { a[2 * i] = tl[i]; b[2 * i] = tr[i]; }
+                jo_dft_exact(a, fl, N, -1); jo_dft_exact(b, fr, N, -1);
+                for (int i = 0; i < N; ++i) {                    /* :263-268 */
+                    R[0][0] += (pow(fl[2 * i], 2.0) + pow(fl[2 * i + 1], 2.0)) / N;
+                    R[0][1] += (-fl[2 * i] * fr[2 * i + 1] + fl[2 * i + 1] * fr[2 * i]) / N;
+                    R[1][0] += (-fr[2 * i] * fl[2 * i + 1] + fr[2 * i + 1] * fl[2 * i]) / N;
+                    R[1][1] += (pow(fr[2 * i], 2.0) + pow(fr[2 * i + 1], 2.0)) / N;
+                }
+            }
+            memcpy(tl, bl, sizeof(bl)); memcpy(tr, br, sizeof(br));
+        } else {
+            iter = 0;
+        }
+        if (corr_out) { corr_out[4 * nb] = R[0][0]; corr_out[4 * nb + 1] = R[0][1]; corr_out[4 * nb + 2] = R[1][0]; corr_out[4 * nb + 3] = R[1][1]; }
+        /* ---- ProcessMVDR (:121-207) */
+        ++calls;
+        memset(a, 0, sizeof(double) * 2 * N); memset(b, 0, sizeof(double) * 2 * N);
+        for (int i = 0; i < K; ++i) { a[2 * i] = keepl[i]; b[2 * i] = keepr[i]; }
+        for (int i = 0; i < B; ++i) { a[2 * (i + K)] = bl[i]; b[2 * (i + K)] = br[i]; }
+        for (int i = 0; i < K; ++i) { keepl[i] = a[2 * (K + i)]; keepr[i] = b[2 * (K + i)]; }   /* :193-194 */
+        jo_dft_exact(a, fl, N, -1); jo_dft_exact(b, fr, N, -1);
+        for (int i = 0; i < N; ++i) {
+            double _Complex Rm[2][2] = {{R[0][0], R[0][1]}, {R[1][0], R[1][1]}}, inv[2][2];
+            const double ang = 2 * pi * i * (fs / N) * dtime;
+            const double _Complex c0 = 1.0, c1 = cos(ang) + sin(ang) * I;
+            jo_inv2(Rm, inv);
+            double _Complex w0 = inv[0][0] * c0 + inv[0][1] * c1, w1 = inv[1][0] * c0 + inv[1][1] * c1;   /* :151 */
+            const double _Complex den = conj(c0) * w0 + conj(c1) * w1;                                     /* :152 */
+            w0 = w0 / den; w1 = w1 / den;
+            const double lw0 = creal(w0), lw1 = -cimag(w0), rw0 = creal(w1), rw1 = -cimag(w1);           /* :156-159 */
+            fl[2 * i] = fl[2 * i] * lw0 - fl[2 * i + 1] * lw1;                                             /* :162 */
+            fl[2 * i + 1] = fl[2 * i] * lw1 + fl[2 * i + 1] * lw0;                                         /* :163 uses the updated real part */
+            fr[2 * i] = fr[2 * i] * rw0 - fr[2 * i + 1] * rw1;
+            fr[2 * i + 1] = fr[2 * i] * rw1 + fr[2 * i + 1] * rw0;
+            a[2 * i] = fl[2 * i] + fr[2 * i];
+            a[2 * i + 1] = fl[2 * i + 1] + fr[2 * i + 1];
+        }
+        jo_dft_exact(a, b, N, +1);
+        if (calls > 1) {                                         /* :202-205 */
+            for (int i = 0; i < B; ++i) out[written + i] = jo_short_of(b[2 * (i + K)] * 1. / N);
+            if (pre_out) for (int i = 0; i < B; ++i) pre_out[written + i] = b[2 * (i + K)] * 1. / N;
+            written += B;
+        }
+        ++nb;
+    }
+    free(a); free(b); free(fl); free(fr);
+    return written;
+}
+
+JO_API int jo_abi_version(void) { return 3; }

@@ -94,6 +94,7 @@ class Oracle:
         L.jo_mfcc_program.restype = C.c_long
         L.jo_pitch_i16.restype = C.c_long
         L.jo_pitch_exact_i16.restype = C.c_long
+        L.jo_mvdr_i16.restype = C.c_long
 
     # ---- FFT ------------------------------------------------------------------------------------
     def bitrev_table(self, n: int) -> np.ndarray:
@@ -197,6 +198,21 @@ class Oracle:
         assert got == nb, (got, nb)
         return arg, mx
 
+    # ---- MVDR ---------------------------------------------------------------------
+    def mvdr(self, xl: np.ndarray, xr: np.ndarray, dtime: float = 0.0):
+        """(out int16, pre-cast double (NaN while the matrix is singular), corr [nb,4] spatial matrix in force for each block,
+        vad [nb]) of BeamForming_MVDR_ver1."""
+        xl, xr = np.ascontiguousarray(xl, np.int16), np.ascontiguousarray(xr, np.int16)
+        n = min(len(xl), len(xr))
+        nb = -(-n // 512)
+        out = np.zeros(max(nb - 1, 0) * 512 + 8, np.int16)
+        pre = np.zeros(max(nb - 1, 0) * 512 + 8, np.float64)
+        corr, vad = np.zeros((max(nb, 1), 4), np.float64), np.zeros(max(nb, 1), np.uint8)
+        w = self.lib.jo_mvdr_i16(_p(xl, C.c_int16), _p(xr, C.c_int16), C.c_long(n), C.c_double(dtime), _p(out, C.c_int16),
+                                 _p(pre, C.c_double), _p(corr, C.c_double), _p(vad, C.c_uint8))
+        assert w == max(nb - 1, 0) * 512, (w, nb)
+        return out[:w], pre[:w], corr[:nb], vad[:nb]
+
     def mfcc_program(self, x: np.ndarray, params: MfccParams) -> np.ndarray:
         x = np.ascontiguousarray(x, np.int16)
         nb = -(-len(x) // (2 * params.hop))
@@ -285,6 +301,16 @@ class RefPrograms:
                 arg.append(int(parts[2]))
                 mx.append(float(parts[4]))
         return np.array(arg, np.int32), np.array(mx, np.float64)
+
+    def mvdr(self, xl: np.ndarray, xr: np.ndarray) -> np.ndarray:
+        """BeamForming_MVDR_ver1 <left.wav> <right.wav> <out.pcm> (angle 0 is hard-wired in the program, :58-60)."""
+        with tempfile.TemporaryDirectory() as d:
+            fl, fr, fo = os.path.join(d, "l.wav"), os.path.join(d, "r.wav"), os.path.join(d, "out.pcm")
+            for fn, x in ((fl, xl), (fr, xr)):
+                with open(fn, "wb") as f:
+                    f.write(self.WAV_HEADER + np.ascontiguousarray(x, np.int16).tobytes())
+            self._run("mvdr_ref", [fl, fr, fo])
+            return np.fromfile(fo, np.int16)
 
     def fftprocess(self, x: np.ndarray, forward: bool) -> np.ndarray:
         """The reference's own FFTProcess built with BLOCK_LEN == len(x) (valid for 2^8..2^15)."""

@@ -76,6 +76,13 @@ def main() -> None:
         pt[f"pcm_{stream}"] = xs
         pt[f"arg_{stream}"], pt[f"rmax_{stream}"] = r.pitch(xs)
     np.savez_compressed(os.path.join(OUT, "pitch.npz"), **pt)
+    # --- MVDR (BeamForming_MVDR_ver1; Eigen served by oracle/eigen_shim) -------------
+    mv = {}
+    for stream in (3, 17):
+        xl, xr = synth.mvdr_pair(stream, 36_000 + 301)
+        mv[f"left_{stream}"], mv[f"right_{stream}"] = xl, xr
+        mv[f"out_{stream}"] = r.mvdr(xl, xr)
+    np.savez_compressed(os.path.join(OUT, "mvdr.npz"), **mv)
     for fn in sorted(os.listdir(OUT)):
         if fn.endswith(".npz"):
             print(fn, os.path.getsize(os.path.join(OUT, fn)), "bytes")

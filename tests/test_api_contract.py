@@ -133,3 +133,46 @@ def test_pitch_contract(be, oracle):
     a, r = be.ctx.pitch(short, p)
     ea, er = oracle.pitch(short, exact=True)
     assert a.shape == (1, 4) and np.array_equal(a[0], ea) and np.array_equal(r[0], er)
+
+
+def test_mvdr_contract(be, oracle):
+    """MVDR entry points: bad presets / framings / shapes are rejected, an empty call is a no-op, padded row pitches work and
+    reset returns the state to 'no block seen' (the first block emits nothing again)."""
+    with pytest.raises(JdspError):
+        be.L.mvdr_params("nope")
+    p = be.L.mvdr_params("ref")
+    assert (p.n_fft, p.block, p.keep, p.energy_thr, p.fs, p.dtime) == (1024, 512, 511, 700.0, 16000.0, 0.0)
+    bad = be.L.mvdr_params("ref"); bad.keep = 512
+    with pytest.raises(JdspError) as e:
+        be.ctx.mvdr_state(bad, 1)
+    assert e.value.code == -4
+    with pytest.raises(JdspError):
+        be.ctx.mvdr_state(p, 0)
+    S, nb, B = 2, 6, 512
+    pairs = [synth.mvdr_pair(s, nb * B) for s in (1, 2)]
+    pitch_in, pitch_out = nb * B + 64, nb * B + 24
+    left, right = np.full((S, pitch_in), 4321, np.int16), np.full((S, pitch_in), -77, np.int16)
+    for s in range(S):
+        left[s, :nb * B], right[s, :nb * B] = pairs[s]
+    st = be.ctx.mvdr_state(p, S)
+    d_l, d_r, d_out = be.to_dev(left), be.to_dev(right), be.zeros((S, pitch_out), np.int16)
+    assert st.run(d_l, d_r, pitch_in, 0, d_out, pitch_out) == 0                   # empty call: nothing happens
+    with pytest.raises(JdspError):
+        st.run(d_l, d_r, pitch_in - 1, nb, d_out, pitch_out)                      # odd row pitch
+    with pytest.raises(JdspError):
+        st.run(d_l, d_r, pitch_in, nb, d_out, (nb - 2) * B)                       # output rows too short
+    runs = []
+    for _ in range(2):
+        d_out = be.zeros((S, pitch_out), np.int16)
+        assert st.run(d_l, d_r, pitch_in, nb, d_out, pitch_out) == nb - 1
+        be.sync()
+        runs.append(be.to_host(d_out).copy())
+        assert st.run(d_l, d_r, pitch_in, nb, d_out, pitch_out) == nb             # a continued stream emits every block
+        be.sync()
+        st.reset()
+    assert np.array_equal(runs[0], runs[1])
+    assert not runs[0][:, (nb - 1) * B:].any()                                    # padding untouched
+    for s in range(S):
+        d = np.abs(runs[0][s, :(nb - 1) * B].astype(int) - oracle.mvdr(*pairs[s])[0].astype(int))
+        assert d.max() <= 1
+    st.close()

@@ -59,3 +59,12 @@ def test_pitch_golden(oracle):
             arg, mx = oracle.pitch(g[f"pcm_{stream}"], exact=exact)
             assert np.array_equal(arg, g[f"arg_{stream}"])
             assert np.allclose(mx, g[f"rmax_{stream}"], rtol=0, atol=1e-6 + 1e-9 * np.abs(mx).max())
+
+
+def test_mvdr_golden(oracle):
+    """BeamForming_MVDR_ver1 outputs of the unmodified program (Eigen served by oracle/eigen_shim): bit-exact."""
+    g = np.load(os.path.join(G, "mvdr.npz"))
+    for stream in (3, 17):
+        out, pre, corr, vad = oracle.mvdr(g[f"left_{stream}"], g[f"right_{stream}"])
+        assert (vad == 0).sum() > 2 and corr[-1, 0] > 0 and corr[-1, 3] > 0, "spatial matrix never estimated: vacuous"
+        assert np.array_equal(out, g[f"out_{stream}"])

@@ -85,3 +85,19 @@ def test_pitch_program(oracle, refprog):
         ea, em = oracle.pitch(x, exact=True)
         assert np.array_equal(ea, oa)
         assert np.abs(em - om).max() <= 1e-9 * max(1.0, np.abs(em).max())
+
+
+def test_mvdr_program(oracle, refprog):
+    """BeamForming_MVDR_ver1: int16 output bit-exact against the unmodified program built over
+    oracle/eigen_shim; also a stream whose matrix never leaves zero (all voice): the program's NaN -> (short) 0."""
+    for s in (5, 6):
+        xl, xr = synth.mvdr_pair(s, 40_000 + 123)
+        out, pre, corr, vad = oracle.mvdr(xl, xr)
+        assert (vad == 0).sum() > 2 and corr[-1, 0] > 0
+        assert np.array_equal(out, refprog.mvdr(xl, xr))
+        # the off-diagonal sums the closed form drops are rounding noise in the program too
+        assert np.abs(corr[:, 1:3]).max() <= 1e-12 * corr[-1, 0]
+    loud = np.random.default_rng(1).normal(0, 3000, 5_000).astype(np.int16)
+    out, pre, corr, vad = oracle.mvdr(loud, loud[::-1].copy())
+    ref = refprog.mvdr(loud, loud[::-1].copy())
+    assert vad.all() and np.array_equal(out, ref) and not ref.any()

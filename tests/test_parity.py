@@ -448,7 +448,7 @@ def test_pitch_dev_chunked_and_edge_inputs(be, oracle):
     st.close()
 
 
-@pytest.mark.parametrize("what", ["denoise_tile", "denoise_stream", "denoise_stream_ref", "pitch", "fft4096"])
+@pytest.mark.parametrize("what", ["denoise_tile", "denoise_stream", "denoise_stream_ref", "pitch", "mvdr", "fft4096"])
 def test_emulator_fiber_order_invariance(what, monkeypatch):
     """Missing-barrier detector for the emulated build: ascending and descending fiber schedules must agree."""
     from backends import EmulBackend
@@ -461,6 +461,9 @@ def test_emulator_fiber_order_invariance(what, monkeypatch):
     elif what == "pitch":
         x = np.stack([synth.denoise_stream(s, 9 * 512) for s in range(3)])
         run = lambda: np.concatenate([a.astype(np.float64) for a in be.ctx.pitch(x, be.L.pitch_params("ref"))], axis=1)
+    elif what == "mvdr":
+        lr = [synth.mvdr_pair(s, 9 * 512) for s in range(3)]
+        run = lambda: be.ctx.mvdr(np.stack([a for a, _ in lr]), np.stack([b for _, b in lr]), be.L.mvdr_params("ref")).copy()
     else:
         z = np.random.default_rng(3).uniform(-1, 1, (3, 4096, 2)).astype(np.float32).view(np.complex64)[..., 0]
         def run():
@@ -473,3 +476,78 @@ def test_emulator_fiber_order_invariance(what, monkeypatch):
         res.append(run())
     be.set_order(+1)
     assert np.array_equal(res[0], res[1])
+
+
+# ---- MVDR beamformer (BeamForming_MVDR_ver1) -------------------------------------------------
+# With a steering delay of 0 the two weights are real and sum to 1, so wherever left[n] == right[n] (about 0.4 / sigma of the
+# difference: 0.5 - 1 % of the samples of these inputs) the exact output IS the integer left[n]; the program's own double
+# arithmetic lands on either side of it by rounding noise and (short) truncates, so about half of those samples differ by one
+# LSB from any other correct evaluation.  The pre-cast floats are held to 1e-4 of the peak (measured 3e-7).
+MVDR_FLIPS = 2e-2
+
+
+def test_mvdr_reference_fixtures(be):
+    """Outputs of the unmodified program (tests/golden/make_golden.py): at most 1 LSB away, on a small share of samples."""
+    g = np.load(os.path.join(G, "mvdr.npz"))
+    left, right = np.stack([g["left_3"], g["left_17"]]), np.stack([g["right_3"], g["right_17"]])
+    out = be.ctx.mvdr(left, right, be.L.mvdr_params("ref"))
+    for i, stream in enumerate((3, 17)):
+        assert out[i].any()
+        assert_i16_parity(out[i], g[f"out_{stream}"], MVDR_FLIPS, f"mvdr fixture {stream}")
+
+
+def test_mvdr_dev_chunked_precast_and_edges(be, oracle):
+    """Device form: VAD decisions, the spatial matrix and the block count are exact; the pre-cast floats stay within 1e-4 of
+    the peak of the oracle's doubles; feeding the stream in chunks changes nothing, bit for bit; streams that are all voice
+    (matrix stays singular), silent on one microphone (singular) or silent on both emit zeros like the program; a steering
+    delay != 0 exercises the per-bin phase and the program's in-place complex product."""
+    rng = np.random.default_rng(31)
+    nb, B = 24, 512
+    pairs = [synth.mvdr_pair(7, nb * B), synth.mvdr_pair(8, nb * B, delay=0, gain=1.0, sigma_r=50.0)]
+    loud = rng.normal(0, 3000, nb * B).astype(np.int16)
+    quiet = rng.normal(0, 30, nb * B).astype(np.int16)
+    pairs += [(loud, loud[::-1].copy()), (quiet, np.zeros(nb * B, np.int16)), (np.zeros(nb * B, np.int16),) * 2,
+              (quiet, rng.integers(-32768, 32768, nb * B).astype(np.int16))]
+    left, right = np.stack([p[0] for p in pairs]), np.stack([p[1] for p in pairs])
+    S = left.shape[0]
+    for dtime in (0.0, 2.5e-4):
+        p = be.L.mvdr_params("ref")
+        p.dtime = dtime
+        st = be.ctx.mvdr_state(p, S)
+        d_l, d_r = be.to_dev(left), be.to_dev(right)
+        d_out, d_f32, d_vad = be.zeros((S, (nb - 1) * B), np.int16), be.zeros((S, (nb - 1) * B), np.float32), be.zeros((S, nb), np.uint8)
+        assert st.run(d_l, d_r, nb * B, nb, d_out, (nb - 1) * B, d_f32, (nb - 1) * B, d_vad) == nb - 1
+        be.sync()
+        out, f32, vad, corr = be.to_host(d_out).copy(), be.to_host(d_f32).copy(), be.to_host(d_vad).copy(), st.spatial_corr()
+        for s in range(S):
+            o_out, o_pre, o_corr, o_vad = oracle.mvdr(left[s], right[s], dtime)
+            assert np.array_equal(vad[s], o_vad), s                                       # integer fact: bit-exact
+            assert np.allclose(corr[s], o_corr[-1, [0, 3]], rtol=1e-12, atol=0), (s, corr[s], o_corr[-1])
+            ok = np.isfinite(o_pre)                                                       # NaN while the matrix is singular
+            assert not out[s][~ok].any() and not o_out[~ok].any()
+            if ok.any():
+                assert_float_parity(f32[s][ok], o_pre[ok], f"mvdr pre-cast {s} dtime {dtime}")
+            assert_i16_parity(out[s], o_out, MVDR_FLIPS, f"mvdr {s} dtime {dtime}")
+        assert out[0].any() and out[1].any() and not out[2].any() and not out[3].any() and not out[4].any()
+        st.reset()
+        parts = []
+        for b0, n in ((0, 1), (1, 2), (3, 14), (17, 7)):
+            c_l, c_r = be.to_dev(left[:, b0 * B:(b0 + n) * B]), be.to_dev(right[:, b0 * B:(b0 + n) * B])
+            emitted = n - (1 if b0 == 0 else 0)
+            c_out = be.zeros((S, max(emitted, 1) * B), np.int16)
+            assert st.run(c_l, c_r, n * B, n, c_out, max(emitted, 1) * B) == emitted
+            be.sync()
+            parts.append(be.to_host(c_out)[:, :emitted * B].copy())
+        assert np.array_equal(np.concatenate(parts, axis=1), out)
+        st.close()
+
+
+def test_mvdr_host_form_stale_tail(be, oracle):
+    """Host form on inputs that are not a whole number of blocks: the fread loop's stale tail and the block count."""
+    for n in (512 * 7 + 100, 300, 512, 0):
+        xl, xr = synth.mvdr_pair(9, max(n, 1))
+        xl, xr = xl[:n], xr[:n]
+        out = be.ctx.mvdr(xl, xr, be.L.mvdr_params("ref"))
+        o_out = oracle.mvdr(xl, xr)[0]
+        assert out.shape == (1, len(o_out))
+        assert_i16_parity(out[0], o_out, MVDR_FLIPS, f"mvdr host n={n}")

@@ -21,7 +21,7 @@ def built():
 
 
 def test_programs_build_without_cuda_headers(built):
-    for p in ("jdsp_fft_roundtrip", "jdsp_denoise", "jdsp_fastconv", "jdsp_mfcc", "jdsp_blockwise", "jdsp_pitch"):
+    for p in ("jdsp_fft_roundtrip", "jdsp_denoise", "jdsp_fastconv", "jdsp_mfcc", "jdsp_blockwise", "jdsp_pitch", "jdsp_mvdr"):
         assert os.path.exists(os.path.join(built, p))
 
 
@@ -108,3 +108,21 @@ def test_pitch_program_prints_the_reference_lines(built, tmp_path, how):
     else:   # a shorter file: whole blocks agree with the fixture, the short last block is checked for the stale-tail rule
         assert np.array_equal(arg[: nb - 1], g["arg_3"][: nb - 1])
     assert np.allclose(pitch, 16000.0 / arg, rtol=0, atol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("how", ["batched", "block"])
+def test_mvdr_program(built, tmp_path, how):
+    """Same argv and file formats as BeamForming_MVDR_ver1; the block-at-a-time form goes through MvdrStream::ProcessMVDR."""
+    g = np.load(os.path.join(G, "mvdr.npz"))
+    fl, fr, fo = tmp_path / "l.wav", tmp_path / "r.wav", tmp_path / "out.pcm"
+    n = len(g["left_3"]) if how == "batched" else 12 * 512 + 100
+    fl.write_bytes(HDR + g["left_3"][:n].tobytes())
+    fr.write_bytes(HDR + g["right_3"][:n].tobytes())
+    _run(built, "jdsp_mvdr", str(fl), str(fr), str(fo), *(["block"] if how == "block" else []))
+    got = np.fromfile(fo, np.int16)
+    nb = -(-n // 512)
+    assert len(got) == (nb - 1) * 512
+    keep = len(got) if how == "batched" else (nb - 2) * 512     # the shorter file's last block has its own stale tail
+    assert got[:keep].any()
+    assert_i16_parity(got[:keep], g["out_3"][:keep], max_flip_frac=2e-2, what=f"mvdr program {how}")
