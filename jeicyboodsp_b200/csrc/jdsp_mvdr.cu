@@ -105,6 +105,29 @@ int jdsp_mvdr_i16_dev(jdsp_ctx *c, jdsp_mvdr_state *st, const int16_t *d_left, c
     REQUIRE(in_pitch >= n_blocks * B && out_pitch >= emitted * B, "row pitch shorter than the payload");
     REQUIRE(!d_out_f32 || f32_pitch >= emitted * B, "f32 row pitch shorter than the payload");
     CU(cudaSetDevice(c->device));
+    // Steering delay 0 (the program's configuration): bin-independent real weights, one pass in the time domain with one warp
+    // per microphone pair.  That walk is sequential in the blocks, so it is chosen when there are pairs enough to fill the GPU
+    // (two warps per SM and up) or the call is short; few long streams take the block-parallel transform path.
+    // JDSP_MVDR_PATH=td|fft overrides the choice (tests run both).
+    const bool aligned = in_pitch % 8 == 0 && out_pitch % 8 == 0 && (((uintptr_t)d_left | (uintptr_t)d_right | (uintptr_t)d_out) & 15) == 0;
+    const char *force = getenv("JDSP_MVDR_PATH");
+    const bool want_td = force ? !strcmp(force, "td") : (S >= 2L * c->sm_count || n_blocks <= 8);
+    if (st->p.dtime == 0.0 && aligned && want_td) {
+        MvdrArgs a{};
+        a.l = d_left; a.r = d_right; a.in_pitch = in_pitch; a.n_blocks = n_blocks;
+        a.out = d_out; a.out_pitch = out_pitch; a.out_f32 = d_out_f32; a.f32_pitch = f32_pitch;
+        a.win_vad = st->d_win; a.st_iter = st->d_iter; a.st_pl = st->d_pl; a.st_pr = st->d_pr; a.st_el = st->d_el; a.st_er = st->d_er;
+        a.vad_out = d_vad; a.n_streams = S; a.energy_thr = st->p.energy_thr; a.skip_blocks = skip;
+        auto kfn = mvdr_td_kernel;
+        JDSP_LAUNCH_PTR(kfn, dim3(grid_for(c, (S + 3) / 4, 16)), dim3(128), 0, c->stream, a);
+        TRY(launch_check(c));
+        CU(cudaMemcpy2DAsync(st->d_prev_l, B * sizeof(int16_t), d_left + (n_blocks - 1) * B, in_pitch * sizeof(int16_t), B * sizeof(int16_t), S,
+                             cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaMemcpy2DAsync(st->d_prev_r, B * sizeof(int16_t), d_right + (n_blocks - 1) * B, in_pitch * sizeof(int16_t), B * sizeof(int16_t), S,
+                             cudaMemcpyDeviceToDevice, c->stream));
+        st->blocks_seen += n_blocks;
+        return JDSP_OK;
+    }
     const size_t items = (size_t)S * n_blocks;
     const size_t need = items * (2 * sizeof(long long) + 2 * sizeof(double)) + ((items + 15) & ~(size_t)15);
     if (st->scratch_bytes < need) {

@@ -17,6 +17,14 @@
 //                      (the imaginary part is formed from the already updated real part, :162-165); inverse transform, real
 //                      part / N of samples [511, 1023), (short).  A singular matrix (no estimate yet, or a silent microphone)
 //                      makes the program emit NaN -> (short) 0: zeros here.
+//
+// Steering delay 0 -- the program's own configuration, its angle is hard-wired to 0 (:58-60) -- makes both weights real and the
+// same for every bin, so the inverse transform of w0 L + w1 R is w0 l[n] + w1 r[n] exactly: no transform is left.
+//   mvdr_td_kernel     ONE pass, one warp per microphone pair walking its blocks in order with the program's state in
+//                      registers (run length, last non-voice energies, the matrix): per block the lanes load the two 512-sample
+//                      blocks (two fully coalesced 16-byte loads per microphone, the next block already in flight), take
+//                      the VAD decision and the energies with three warp reductions, update the matrix exactly like the scan
+//                      kernel, and write w0 l + w1 r.  Every sample crosses HBM once in and once out: 6 bytes per sample pair.
 #pragma once
 #include "kernels_stft.cuh"
 
@@ -173,6 +181,132 @@ __global__ void __launch_bounds__(MvdrGeom::NT) mvdr_apply_kernel(MvdrArgs a) {
                 }
             }
         }
+    }
+}
+
+// ---- steering delay 0: single pass in the time domain --------------------------------------------------------------------
+struct MvdrBlockRegs { uint4 l0, l1, r0, r1; };   // lane t holds samples [8t, 8t+8) and [256+8t, 256+8t+8) of both microphones
+
+JDSP_DEV MvdrBlockRegs mvdr_load_block(const int16_t *l, const int16_t *r, int t) {
+    MvdrBlockRegs v;
+    const uint4 *pl = reinterpret_cast<const uint4 *>(l), *pr = reinterpret_cast<const uint4 *>(r);
+    v.l0 = pl[t]; v.l1 = pl[32 + t]; v.r0 = pr[t]; v.r1 = pr[32 + t];
+    return v;
+}
+// The conversion unit (I2F / F2I: 16 lanes per clock per SM, profiles/microbench) would bound this kernel ahead of HBM, so
+// int16 -> float and |int16| -> double go through the exponent trick on the ALU / FP pipes instead: exact for these ranges.
+JDSP_DEV float s16_to_f32(unsigned u16) {            // u16 = the sample's 16 bits
+    return __int_as_float((int)(0x4B000000u | (u16 ^ 0x8000u))) - 8421376.0f;     // 2^23 + (x + 32768) - (2^23 + 32768)
+}
+JDSP_DEV double u16_to_f64(unsigned mag) {           // mag = |x| <= 32768
+    return __hiloint2double(0x43300000, (int)mag) - 4503599627370496.0;             // 2^52 + mag - 2^52
+}
+JDSP_DEV unsigned warp_sum_u32(unsigned v) {
+#ifdef JDSP_EMUL
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+#else
+    return __reduce_add_sync(0xffffffffu, v);
+#endif
+}
+// sum over the warp of per-lane values below 2^40: two 32-bit reductions (REDUX) instead of five 64-bit shuffle rounds
+JDSP_DEV long long warp_sum_u40(unsigned long long v) {
+    const unsigned lo = warp_sum_u32((unsigned)(v & 0xffffffu)), hi = warp_sum_u32((unsigned)(v >> 24));
+    return (long long)(((unsigned long long)hi << 24) + lo);
+}
+// a shared-memory load the compiler may not hoist out of the block loop (it would keep 16 doubles per lane live and spill them)
+JDSP_DEV double2 lds_f64x2(const double *p) {
+#ifdef JDSP_EMUL
+    return *reinterpret_cast<const double2 *>(p);
+#else
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return v;
+#endif
+}
+// VAD energy and block energies of 8 samples per microphone (one 16-byte word each)
+JDSP_DEV void mvdr_td_stats8(const uint4 &vl, const uint4 &vr, const double *w, unsigned long long &ev, unsigned long long &sl,
+                             unsigned long long &sr) {
+    const unsigned wl[4] = {vl.x, vl.y, vl.z, vl.w}, wr[4] = {vr.x, vr.y, vr.z, vr.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double2 ww = lds_f64x2(w + 2 * i);
+        const int l0 = (int)(int16_t)(wl[i] & 0xffffu), l1 = (int)wl[i] >> 16, r0 = (int)(int16_t)(wr[i] & 0xffffu), r1 = (int)wr[i] >> 16;
+        // (short)(x * w) (:224): the square only needs |trunc(x w)| = trunc(|x| w)
+        const unsigned v0 = (unsigned)__double2int_rz(u16_to_f64((unsigned)abs(l0)) * ww.x);
+        const unsigned v1 = (unsigned)__double2int_rz(u16_to_f64((unsigned)abs(l1)) * ww.y);
+        ev += (unsigned long long)(v0 * v0) + (unsigned long long)(v1 * v1);                   // :228, each square < 2^31
+        sl += (unsigned long long)(unsigned)(l0 * l0) + (unsigned long long)(unsigned)(l1 * l1);
+        sr += (unsigned long long)(unsigned)(r0 * r0) + (unsigned long long)(unsigned)(r1 * r1);
+    }
+}
+JDSP_DEV uint4 mvdr_td_mix8(const uint4 &vl, const uint4 &vr, float w0, float g1, float *f32) {
+    const unsigned wl[4] = {vl.x, vl.y, vl.z, vl.w}, wr[4] = {vr.x, vr.y, vr.z, vr.w};
+    unsigned o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float y0 = fmaf(w0, s16_to_f32(wl[i] & 0xffffu), g1 * s16_to_f32(wr[i] & 0xffffu));
+        const float y1 = fmaf(w0, s16_to_f32(wl[i] >> 16), g1 * s16_to_f32(wr[i] >> 16));
+        o[i] = ((unsigned)(uint16_t)trunc16(y0)) | ((unsigned)(uint16_t)trunc16(y1) << 16);
+        if (f32) { f32[2 * i] = y0; f32[2 * i + 1] = y1; }
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+__global__ void __launch_bounds__(128, 7) mvdr_td_kernel(MvdrArgs a) {
+    constexpr int B = MvdrGeom::B, N = MvdrGeom::N;
+    __shared__ __align__(16) double win_s[B];                // VAD window, w[511 + i]
+    for (int i = threadIdx.x; i < B; i += blockDim.x) win_s[i] = a.win_vad[i];
+    __syncthreads();
+    const int t = threadIdx.x % 32;
+    const long warp = (long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, n_warps = (long)gridDim.x * (blockDim.x / 32);
+    for (long s = warp; s < a.n_streams; s += n_warps) {
+        const int16_t *l = a.l + s * a.in_pitch, *r = a.r + s * a.in_pitch;
+        int iter = a.st_iter[s];
+        long long pl = a.st_pl[s], pr = a.st_pr[s];
+        double el = a.st_el[s], er = a.st_er[s];
+        const long nb = a.n_blocks;
+        MvdrBlockRegs cur = mvdr_load_block(l, r, t);
+        for (long b = 0; b < nb; ++b) {
+            const long bn = b + 1 < nb ? b + 1 : b;           // the next block is in flight while this one is processed
+            const MvdrBlockRegs nxt = mvdr_load_block(l + bn * B, r + bn * B, t);
+            // ---- VAD on the left block (:209-243) and the block energies
+            unsigned long long ev = 0, sl = 0, sr = 0;
+            mvdr_td_stats8(cur.l0, cur.r0, win_s + 8 * t, ev, sl, sr);
+            mvdr_td_stats8(cur.l1, cur.r1, win_s + 256 + 8 * t, ev, sl, sr);
+            const long long evs = warp_sum_u40(ev), sls = warp_sum_u40(sl), srs = warp_sum_u40(sr);
+            const bool voice = (double)evs / (double)N > a.energy_thr;                        // :235-238
+            // ---- main's state machine (:95-108), identical on every lane
+            if (!voice) {
+                ++iter;
+                if (iter > 1) { el += (double)(pl + sls); er += (double)(pr + srs); }
+                pl = sls; pr = srs;
+            } else {
+                iter = 0;
+            }
+            if (a.vad_out && t == 0) a.vad_out[s * nb + b] = voice ? 1 : 0;
+            // ---- ProcessMVDR with bin-independent real weights
+            const long ob = b - a.skip_blocks;
+            if (ob >= 0) {
+                const bool singular = !(el > 0.0) || !(er > 0.0);
+                const float w0 = singular ? 0.f : (float)(er / (el + er)), g1 = singular ? 0.f : (float)(el / (el + er));
+                uint4 *po = reinterpret_cast<uint4 *>(a.out + s * a.out_pitch + ob * B);
+                if (a.out_f32) {
+                    float y[16];
+                    float *pf = a.out_f32 + s * a.f32_pitch + ob * B;
+                    po[t] = mvdr_td_mix8(cur.l0, cur.r0, w0, g1, y);
+                    po[32 + t] = mvdr_td_mix8(cur.l1, cur.r1, w0, g1, y + 8);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { pf[8 * t + j] = y[j]; pf[256 + 8 * t + j] = y[8 + j]; }
+                } else {
+                    po[t] = mvdr_td_mix8(cur.l0, cur.r0, w0, g1, nullptr);
+                    po[32 + t] = mvdr_td_mix8(cur.l1, cur.r1, w0, g1, nullptr);
+                }
+            }
+            cur = nxt;
+        }
+        if (t == 0) { a.st_iter[s] = iter; a.st_pl[s] = pl; a.st_pr[s] = pr; a.st_el[s] = el; a.st_er[s] = er; }
     }
 }
 

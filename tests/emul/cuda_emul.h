@@ -139,6 +139,9 @@ static inline int __float2int_rz(float x) { return (int)x; }
 static inline int __double2int_rz(double x) { return (int)x; }
 static inline float __int2float_rn(int x) { return (float)x; }
 static inline double __int2double_rn(int x) { return (double)x; }
+static inline double __hiloint2double(int hi, int lo) {
+    unsigned long long u = ((unsigned long long)(unsigned)hi << 32) | (unsigned)lo; double d; memcpy(&d, &u, 8); return d;
+}
 static inline float __int_as_float(int x) { float f; memcpy(&f, &x, 4); return f; }
 static inline int __float_as_int(float f) { int x; memcpy(&x, &f, 4); return x; }
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }

@@ -448,7 +448,7 @@ def test_pitch_dev_chunked_and_edge_inputs(be, oracle):
     st.close()
 
 
-@pytest.mark.parametrize("what", ["denoise_tile", "denoise_stream", "denoise_stream_ref", "pitch", "mvdr", "fft4096"])
+@pytest.mark.parametrize("what", ["denoise_tile", "denoise_stream", "denoise_stream_ref", "pitch", "mvdr_td", "mvdr_fft", "fft4096"])
 def test_emulator_fiber_order_invariance(what, monkeypatch):
     """Missing-barrier detector for the emulated build: ascending and descending fiber schedules must agree."""
     from backends import EmulBackend
@@ -461,7 +461,8 @@ def test_emulator_fiber_order_invariance(what, monkeypatch):
     elif what == "pitch":
         x = np.stack([synth.denoise_stream(s, 9 * 512) for s in range(3)])
         run = lambda: np.concatenate([a.astype(np.float64) for a in be.ctx.pitch(x, be.L.pitch_params("ref"))], axis=1)
-    elif what == "mvdr":
+    elif what.startswith("mvdr"):
+        monkeypatch.setenv("JDSP_MVDR_PATH", what[5:])
         lr = [synth.mvdr_pair(s, 9 * 512) for s in range(3)]
         run = lambda: be.ctx.mvdr(np.stack([a for a, _ in lr]), np.stack([b for _, b in lr]), be.L.mvdr_params("ref")).copy()
     else:
@@ -486,8 +487,11 @@ def test_emulator_fiber_order_invariance(what, monkeypatch):
 MVDR_FLIPS = 2e-2
 
 
-def test_mvdr_reference_fixtures(be):
-    """Outputs of the unmodified program (tests/golden/make_golden.py): at most 1 LSB away, on a small share of samples."""
+@pytest.mark.parametrize("path", ["td", "fft"])
+def test_mvdr_reference_fixtures(be, monkeypatch, path):
+    """Outputs of the unmodified program (tests/golden/make_golden.py): at most 1 LSB away, on a small share of samples;
+    through the single-pass time-domain kernel (steering delay 0) and through the transform kernels."""
+    monkeypatch.setenv("JDSP_MVDR_PATH", path)
     g = np.load(os.path.join(G, "mvdr.npz"))
     left, right = np.stack([g["left_3"], g["left_17"]]), np.stack([g["right_3"], g["right_17"]])
     out = be.ctx.mvdr(left, right, be.L.mvdr_params("ref"))
@@ -496,11 +500,13 @@ def test_mvdr_reference_fixtures(be):
         assert_i16_parity(out[i], g[f"out_{stream}"], MVDR_FLIPS, f"mvdr fixture {stream}")
 
 
-def test_mvdr_dev_chunked_precast_and_edges(be, oracle):
+@pytest.mark.parametrize("path", ["td", "fft"])
+def test_mvdr_dev_chunked_precast_and_edges(be, oracle, monkeypatch, path):
     """Device form: VAD decisions, the spatial matrix and the block count are exact; the pre-cast floats stay within 1e-4 of
     the peak of the oracle's doubles; feeding the stream in chunks changes nothing, bit for bit; streams that are all voice
     (matrix stays singular), silent on one microphone (singular) or silent on both emit zeros like the program; a steering
     delay != 0 exercises the per-bin phase and the program's in-place complex product."""
+    monkeypatch.setenv("JDSP_MVDR_PATH", path)
     rng = np.random.default_rng(31)
     nb, B = 24, 512
     pairs = [synth.mvdr_pair(7, nb * B), synth.mvdr_pair(8, nb * B, delay=0, gain=1.0, sigma_r=50.0)]
@@ -540,6 +546,29 @@ def test_mvdr_dev_chunked_precast_and_edges(be, oracle):
             parts.append(be.to_host(c_out)[:, :emitted * B].copy())
         assert np.array_equal(np.concatenate(parts, axis=1), out)
         st.close()
+
+
+def test_mvdr_paths_agree_and_many_streams(be, oracle, monkeypatch):
+    """More microphone pairs than one CTA holds (the time-domain kernel's warp-per-pair walk, several CTAs) against the
+    transform path: VAD decisions and the spatial matrix identical, samples at most 1 LSB apart; spot checks vs the oracle."""
+    S, nb, B = (600 if be.name == "gpu" else 11), 12, 512
+    pairs = [synth.mvdr_pair(100 + s, nb * B, delay=s % 5, gain=0.6 + 0.05 * (s % 9)) for s in range(S)]
+    left, right = np.stack([p[0] for p in pairs]), np.stack([p[1] for p in pairs])
+    res = {}
+    for path in ("td", "fft"):
+        monkeypatch.setenv("JDSP_MVDR_PATH", path)
+        st = be.ctx.mvdr_state(be.L.mvdr_params("ref"), S)
+        d_out, d_vad = be.zeros((S, (nb - 1) * B), np.int16), be.zeros((S, nb), np.uint8)
+        assert st.run(be.to_dev(left), be.to_dev(right), nb * B, nb, d_out, (nb - 1) * B, None, 0, d_vad) == nb - 1
+        be.sync()
+        res[path] = (be.to_host(d_out).copy(), be.to_host(d_vad).copy(), st.spatial_corr())
+        st.close()
+    assert np.array_equal(res["td"][1], res["fft"][1]) and np.array_equal(res["td"][2], res["fft"][2])
+    assert np.abs(res["td"][0].astype(int) - res["fft"][0].astype(int)).max() <= 1
+    for s in (0, S // 2, S - 1):
+        o_out, _, o_corr, o_vad = oracle.mvdr(left[s], right[s])
+        assert np.array_equal(res["td"][1][s], o_vad)
+        assert_i16_parity(res["td"][0][s], o_out, MVDR_FLIPS, f"mvdr td {s}")
 
 
 def test_mvdr_host_form_stale_tail(be, oracle):
