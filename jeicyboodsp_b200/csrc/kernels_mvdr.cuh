@@ -225,20 +225,29 @@ JDSP_DEV double2 lds_f64x2(const double *p) {
     return v;
 #endif
 }
-// VAD energy and block energies of 8 samples per microphone (one 16-byte word each)
-JDSP_DEV void mvdr_td_stats8(const uint4 &vl, const uint4 &vr, const double *w, unsigned long long &ev, unsigned long long &sl,
-                             unsigned long long &sr) {
-    const unsigned wl[4] = {vl.x, vl.y, vl.z, vl.w}, wr[4] = {vr.x, vr.y, vr.z, vr.w};
+#ifndef JDSP_MVDR_LAZY
+#define JDSP_MVDR_LAZY 1       // 1: block energies only for non-voice blocks (the only ones the spatial matrix uses, :95-105)
+#endif
+// VAD energy of 8 left samples (one 16-byte word): sum of (short)(x * w)^2 (:224-228)
+JDSP_DEV void mvdr_td_vad8(const uint4 &vl, const double *w, unsigned long long &ev) {
+    const unsigned wl[4] = {vl.x, vl.y, vl.z, vl.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const double2 ww = lds_f64x2(w + 2 * i);
-        const int l0 = (int)(int16_t)(wl[i] & 0xffffu), l1 = (int)wl[i] >> 16, r0 = (int)(int16_t)(wr[i] & 0xffffu), r1 = (int)wr[i] >> 16;
-        // (short)(x * w) (:224): the square only needs |trunc(x w)| = trunc(|x| w)
+        const double2 ww = lds_f64x2(w + 64 * i);            // [word][lane] pairs: consecutive lanes read consecutive 16 bytes
+        const int l0 = (int)(int16_t)(wl[i] & 0xffffu), l1 = (int)wl[i] >> 16;
+        // the square only needs |trunc(x w)| = trunc(|x| w)
         const unsigned v0 = (unsigned)__double2int_rz(u16_to_f64((unsigned)abs(l0)) * ww.x);
         const unsigned v1 = (unsigned)__double2int_rz(u16_to_f64((unsigned)abs(l1)) * ww.y);
         ev += (unsigned long long)(v0 * v0) + (unsigned long long)(v1 * v1);                   // :228, each square < 2^31
-        sl += (unsigned long long)(unsigned)(l0 * l0) + (unsigned long long)(unsigned)(l1 * l1);
-        sr += (unsigned long long)(unsigned)(r0 * r0) + (unsigned long long)(unsigned)(r1 * r1);
+    }
+}
+// sum of squares of 8 samples
+JDSP_DEV void mvdr_td_energy8(const uint4 &v, unsigned long long &acc) {
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int x0 = (int)(int16_t)(w[i] & 0xffffu), x1 = (int)w[i] >> 16;
+        acc += (unsigned long long)(unsigned)(x0 * x0) + (unsigned long long)(unsigned)(x1 * x1);
     }
 }
 JDSP_DEV uint4 mvdr_td_mix8(const uint4 &vl, const uint4 &vr, float w0, float g1, float *f32) {
@@ -256,8 +265,10 @@ JDSP_DEV uint4 mvdr_td_mix8(const uint4 &vl, const uint4 &vr, float w0, float g1
 
 __global__ void __launch_bounds__(128, 7) mvdr_td_kernel(MvdrArgs a) {
     constexpr int B = MvdrGeom::B, N = MvdrGeom::N;
-    __shared__ __align__(16) double win_s[B];                // VAD window, w[511 + i]
-    for (int i = threadIdx.x; i < B; i += blockDim.x) win_s[i] = a.win_vad[i];
+    // VAD window w[511 + n], stored in the order the lanes read it: sample n = 256 q + 8 t + 2 i + e sits at ((4 q + i) 32 + t) 2 + e
+    // (lane-contiguous 16-byte reads; the natural order cost 4-way bank conflicts: 251 M of 336 M wavefronts in ncu)
+    __shared__ __align__(16) double win_s[B];
+    for (int n = threadIdx.x; n < B; n += blockDim.x) win_s[(((n >> 8) * 4 + ((n >> 1) & 3)) * 32 + ((n >> 3) & 31)) * 2 + (n & 1)] = a.win_vad[n];
     __syncthreads();
     const int t = threadIdx.x % 32;
     const long warp = (long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, n_warps = (long)gridDim.x * (blockDim.x / 32);
@@ -272,13 +283,23 @@ __global__ void __launch_bounds__(128, 7) mvdr_td_kernel(MvdrArgs a) {
             const long bn = b + 1 < nb ? b + 1 : b;           // the next block is in flight while this one is processed
             const MvdrBlockRegs nxt = mvdr_load_block(l + bn * B, r + bn * B, t);
             // ---- VAD on the left block (:209-243) and the block energies
-            unsigned long long ev = 0, sl = 0, sr = 0;
-            mvdr_td_stats8(cur.l0, cur.r0, win_s + 8 * t, ev, sl, sr);
-            mvdr_td_stats8(cur.l1, cur.r1, win_s + 256 + 8 * t, ev, sl, sr);
-            const long long evs = warp_sum_u40(ev), sls = warp_sum_u40(sl), srs = warp_sum_u40(sr);
+            unsigned long long ev = 0;
+            mvdr_td_vad8(cur.l0, win_s + 2 * t, ev);
+            mvdr_td_vad8(cur.l1, win_s + 256 + 2 * t, ev);
+            const long long evs = warp_sum_u40(ev);
             const bool voice = (double)evs / (double)N > a.energy_thr;                        // :235-238
+#if !JDSP_MVDR_LAZY
+            unsigned long long sl = 0, sr = 0;
+            mvdr_td_energy8(cur.l0, sl); mvdr_td_energy8(cur.l1, sl); mvdr_td_energy8(cur.r0, sr); mvdr_td_energy8(cur.r1, sr);
+            const long long sls = warp_sum_u40(sl), srs = warp_sum_u40(sr);
+#endif
             // ---- main's state machine (:95-108), identical on every lane
             if (!voice) {
+#if JDSP_MVDR_LAZY
+                unsigned long long sl = 0, sr = 0;
+                mvdr_td_energy8(cur.l0, sl); mvdr_td_energy8(cur.l1, sl); mvdr_td_energy8(cur.r0, sr); mvdr_td_energy8(cur.r1, sr);
+                const long long sls = warp_sum_u40(sl), srs = warp_sum_u40(sr);
+#endif
                 ++iter;
                 if (iter > 1) { el += (double)(pl + sls); er += (double)(pr + srs); }
                 pl = sls; pr = srs;

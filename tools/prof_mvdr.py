@@ -15,8 +15,9 @@ ap.add_argument("--streams", type=int, default=4096)
 ap.add_argument("--seconds", type=float, default=20.0)
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--dtime", type=float, default=0.0)
+ap.add_argument("--lib", default=None)
 a = ap.parse_args()
-L = Library()
+L = Library(a.lib)
 ctx = Context(L, 0, stream=torch.cuda.current_stream().cuda_stream)
 p = L.mvdr_params("ref")
 p.dtime = a.dtime
