@@ -15,3 +15,4 @@ if [ $RC -eq 0 ]; then
   ncu --set full --clock-control none --import-source on -k regex:mvdr_ -s 1 -c 1 -o gpurun_out/mvdr_td_$TAG python tools/prof_mvdr.py --iters 2 > gpurun_out/ncu_mvdr_$TAG.log 2>&1
   tail -2 gpurun_out/ncu_mvdr_$TAG.log
 fi
+JDSP_MVDR_PATH=fft ncu --set full --clock-control none --import-source on -k regex:mvdr_apply -s 1 -c 1 -o gpurun_out/mvdr_fft_$TAG python tools/prof_mvdr.py --iters 2 > /dev/null 2>&1
