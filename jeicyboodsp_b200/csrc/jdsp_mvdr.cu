@@ -161,6 +161,8 @@ int jdsp_mvdr_i16_dev(jdsp_ctx *c, jdsp_mvdr_state *st, const int16_t *d_left, c
     {   // ProcessMVDR, frame-parallel
         auto kfn = mvdr_apply_kernel;
         TRY(opt_in_smem(kfn, MvdrGeom::SMEM));
+        // 4 CTAs x 33 KB per SM: ask for the large shared-memory carve-out (the default split left room for 3)
+        CU(cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         JDSP_LAUNCH_PTR(kfn, dim3(grid_for(c, ((long)items + MvdrGeom::WARPS - 1) / MvdrGeom::WARPS, 4)), dim3(MvdrGeom::NT), MvdrGeom::SMEM,
                         c->stream, a);
         TRY(launch_check(c));

@@ -348,8 +348,11 @@ __global__ void __launch_bounds__(MfccGeom<NC>::NT) mfcc_kernel(MfccArgs a) {
         }
         __syncthreads();  // (E)
         // ---- M4 DCT (:176-183) with M5 lifter (:185-192) folded into the table ------------------------------
-        for (int it = tid; it < nf * NCEP; it += NT) {
-            const int f = it / NCEP, i = it % NCEP;
+        // items are (frame, slot) with DP = 16 slots per frame, slots >= n_cep idle: a shift and a mask instead of a division
+        // by the run-time n_cep (the division routine was 18 % of the kernel's instructions, ncu source view)
+        for (int it = tid; it < nf * DP; it += NT) {
+            const int f = it / DP, i = it % DP;
+            if (i >= NCEP) continue;
             const float *ml = mel + f * MAXMEL;
             float acc = 0.f;
             float acc1 = 0.f;

@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(128) mvdr_scan_kernel(MvdrArgs a) {
     a.st_iter[s] = iter; a.st_pl[s] = pl; a.st_pr[s] = pr; a.st_el[s] = el; a.st_er[s] = er;
 }
 
-__global__ void __launch_bounds__(MvdrGeom::NT) mvdr_apply_kernel(MvdrArgs a) {
+__global__ void __launch_bounds__(MvdrGeom::NT, 4) mvdr_apply_kernel(MvdrArgs a) {
     using Geo = MvdrGeom;
     constexpr int N = Geo::N, B = Geo::B, K = Geo::K, E = Geo::E, G = Geo::G;
     JDSP_DYN_SMEM(smem_raw);
