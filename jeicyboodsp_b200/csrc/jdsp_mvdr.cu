@@ -158,7 +158,22 @@ int jdsp_mvdr_i16_dev(jdsp_ctx *c, jdsp_mvdr_state *st, const int16_t *d_left, c
         JDSP_LAUNCH_PTR(kfn, dim3((unsigned)((S + 127) / 128)), dim3(128), 0, c->stream, a);
         TRY(launch_check(c));
     }
-    {   // ProcessMVDR, frame-parallel
+    // ProcessMVDR, frame-parallel: the right-channel-only packed transform when the output rows allow 4-byte stores
+    // (JDSP_MVDR_APPLY=full forces the two-microphone complex transform; tests run both)
+    const char *apply = getenv("JDSP_MVDR_APPLY");
+    const bool rows32 = out_pitch % 2 == 0 && (((uintptr_t)d_out) & 3) == 0 && (!d_out_f32 || (f32_pitch % 2 == 0 && (((uintptr_t)d_out_f32) & 7) == 0));
+    if (rows32 && !(apply && !strcmp(apply, "full"))) {
+        void *tw512, *twr512;
+        TRY(get_table(c, 0, 512, &tw512));
+        TRY(get_table(c, 2, 512, &twr512));
+        a.tw = (const cf *)tw512; a.twr = (const float2 *)twr512;
+        auto kfn = mvdr_apply_r_kernel;
+        TRY(opt_in_smem(kfn, MvdrRGeom::SMEM));
+        CU(cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        JDSP_LAUNCH_PTR(kfn, dim3(grid_for(c, ((long)items + MvdrRGeom::WARPS - 1) / MvdrRGeom::WARPS, 6)), dim3(MvdrRGeom::NT), MvdrRGeom::SMEM,
+                        c->stream, a);
+        TRY(launch_check(c));
+    } else {
         auto kfn = mvdr_apply_kernel;
         TRY(opt_in_smem(kfn, MvdrGeom::SMEM));
         // 4 CTAs x 33 KB per SM: ask for the large shared-memory carve-out (the default split left room for 3)

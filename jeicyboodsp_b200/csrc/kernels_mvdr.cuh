@@ -35,7 +35,8 @@ struct MvdrArgs {
     int16_t *out; long out_pitch;
     float *out_f32; long f32_pitch;
     const double *win_vad;         // [B]   w[511 + i]
-    const cf *tw;                  // pass twiddles for length 1024, 32 points per thread
+    const cf *tw;                  // pass twiddles: length 1024 with 32 points per thread (apply), length 512 with 16 (apply_r)
+    const float2 *twr;             // (cos, sin)(2 pi k / 1024), k <= 256: real-transform post-twiddle (apply_r)
     const float2 *steer;           // [N]   (cos, sin) theta_i
     // per-stream state
     const int16_t *st_prev_l, *st_prev_r;   // [stream][B] previous block (zeros before the first)
@@ -179,6 +180,130 @@ __global__ void __launch_bounds__(MvdrGeom::NT, 4) mvdr_apply_kernel(MvdrArgs a)
                     orow[n - K] = trunc16(v);
                     if (frow) frow[n - K] = v;
                 }
+            }
+        }
+    }
+}
+
+// ---- any steering delay, half the transform work ---------------------------------------------------------------------------
+// The left weight conj(w0) = ER / (EL + ER) is real and the same for every bin whatever the delay (and the program's in-place
+// product with an imaginary part of -0 is the plain real scaling), so the left microphone contributes w0 l[n] in the time
+// domain and only the RIGHT frame is transformed: a packed real transform (512 complex points, 16 per thread) instead of a
+// 1024-point complex one.  The weighted right spectrum R'_i = inplace(R_i, conj w1_i) is NOT Hermitian (theta_i runs over all
+// i < N, :147-148, and the in-place product is not a complex product), but only Re(IFFT) is written (:189-191), and that is
+// the inverse of the Hermitian part H_i = (R'_i + conj R'_{N-i}) / 2: a packed real inverse.
+struct MvdrRGeom {
+    static constexpr int NC = 512, N = 1024, B = 512, K = 511, E = 16, G = NC / E, WARPS = 4, NT = WARPS * 32;
+    static constexpr int PADN = padded_len(NC), GBUF = PADN + 1;
+    static constexpr int NTW = TwLayout<NC, E>::total;
+    static constexpr size_t OFF_TW = ((size_t)WARPS * GBUF * sizeof(cf) + 15) & ~(size_t)15;
+    static constexpr size_t OFF_TWR = (OFF_TW + (size_t)NTW * sizeof(cf) + 15) & ~(size_t)15;
+    static constexpr size_t SMEM = OFF_TWR + (size_t)(NC / 2 + 2) * sizeof(float2);
+    static_assert(G == 32, "one warp per frame");
+};
+// the program's in-place product (:164-165) of R with conj(w1) = g1 (cos, -sin): kept as (rw0, rw1) = (g1 cos, -g1 sin)
+JDSP_DEV cf mvdr_inplace(cf R, float g1, float2 cs) {
+    const float rw0 = g1 * cs.x, rw1 = -(g1 * cs.y);
+    const float re = R.x * rw0 - R.y * rw1;
+    return cmake<float>(re, re * rw1 + R.y * rw0);             // the imaginary part uses the already updated real part
+}
+// H_i / N for bin i <= N/2 from R_i (R_{N-i} = conj R_i for the real frame)
+JDSP_DEV cf mvdr_hermitian_bin(cf R, int i, float g1, const float2 *steer, float half_inv_n) {
+    const cf A = mvdr_inplace(R, g1, steer[i]);
+    const cf Bq = mvdr_inplace(cmake<float>(R.x, -R.y), g1, steer[(MvdrRGeom::N - i) & (MvdrRGeom::N - 1)]);
+    return cmake<float>((A.x + Bq.x) * half_inv_n, (A.y - Bq.y) * half_inv_n);
+}
+
+__global__ void __launch_bounds__(MvdrRGeom::NT) mvdr_apply_r_kernel(MvdrArgs a) {
+    using Geo = MvdrRGeom;
+    constexpr int NC = Geo::NC, N = Geo::N, B = Geo::B, E = Geo::E, G = Geo::G, HM = E / 2, NT = Geo::NT;
+    constexpr int MSTRIDE = G + G / 16;
+    JDSP_DYN_SMEM(smem_raw);
+    cf *tw = reinterpret_cast<cf *>(smem_raw + Geo::OFF_TW);
+    float2 *twr = reinterpret_cast<float2 *>(smem_raw + Geo::OFF_TWR);
+    for (int i = threadIdx.x; i < Geo::NTW; i += NT) tw[i] = a.tw[i];
+    for (int i = threadIdx.x; i <= NC / 2; i += NT) twr[i] = a.twr[i];
+    __syncthreads();
+    const int w = threadIdx.x / 32, t = threadIdx.x % 32;
+    cf *buf = reinterpret_cast<cf *>(smem_raw) + w * Geo::GBUF;
+    cf *own = buf + pad16(t);
+    cf *mir = buf + pad16(NC - t);
+    const float inv_n = 1.0f / (float)N, half_inv_n = 0.5f * inv_n;
+    const long n_items = a.n_streams * a.n_blocks;
+    StridedDivmod dm((long)blockIdx.x * Geo::WARPS + w, (long)gridDim.x * Geo::WARPS, a.n_blocks);
+    for (long item = (long)blockIdx.x * Geo::WARPS + w; item < n_items; item += (long)gridDim.x * Geo::WARPS, dm.next()) {
+        const long s = dm.q, b = dm.r;
+        const uint32_t *cl = reinterpret_cast<const uint32_t *>(a.l + s * a.in_pitch + b * B);
+        const uint32_t *cr = reinterpret_cast<const uint32_t *>(a.r + s * a.in_pitch + b * B);
+        const uint32_t *pr = b > 0 ? cr - B / 2 : reinterpret_cast<const uint32_t *>(a.st_prev_r + s * B);
+        // ---- right frame x = [first 511 samples of the previous block | block | 0] (:136-141,193-194), packed
+        //      z[n] = x[2n] + j x[2n+1], half-scaled for untangle2x; the block starts at the odd position 511
+        cf reg[E];
+#pragma unroll
+        for (int m = 0; m < HM; ++m) {
+            const int n = t + G * m;
+            uint32_t wd = pr[n];                                                  // x[2n], x[2n+1] = prev[2n], prev[2n+1]
+            if (m == HM - 1 && t == 31) wd = (wd & 0xffffu) | (cr[0] << 16);      // n = 255: x[510] = prev[510], x[511] = block[0]
+            reg[m] = cmake<float>(0.5f * s16lo(wd), 0.5f * s16hi(wd));
+        }
+#pragma unroll
+        for (int m = HM; m < E; ++m) {
+            const int j = t + G * (m - HM);                                       // n = 256 + j: x[2n] = block[2j+1], x[2n+1] = block[2j+2]
+            const uint32_t wa = cr[j], wb = j < B / 2 - 1 ? cr[j + 1] : 0u;       // x[1023] = 0
+            reg[m] = cmake<float>(0.5f * s16hi(wa), 0.5f * s16lo(wb));
+        }
+        __syncwarp();
+        group_fft<float, NC, E, false, 0>(reg, t, buf, tw);
+        group_sync<0>();
+#pragma unroll
+        for (int m = HM; m < E; ++m) own[m * MSTRIDE] = reg[m];
+        if (t == 0) buf[Geo::PADN] = reg[0];
+        // ---- weights of this block (:144-152 in closed form for a diagonal matrix)
+        const double el = a.el[item], er = a.er[item];
+        const bool singular = !(el > 0.0) || !(er > 0.0);
+        const float w0 = singular ? 0.f : (float)(er / (el + er)), g1 = singular ? 0.f : (float)(el / (el + er));
+        {   // bin NC/2 = 256 (thread 0, m = 8) pairs with itself: R = 2 conj(A), Z' = 2 conj(Y)
+            const cf R = cmake<float>(2.f * reg[HM].x, -2.f * reg[HM].y);
+            const cf Y = mvdr_hermitian_bin(R, NC / 2, g1, a.steer, half_inv_n);
+            reg[HM] = cmake<float>(2.f * Y.x, -2.f * Y.y);
+        }
+        group_sync<0>();
+#pragma unroll
+        for (int m = 0; m < HM; ++m) {
+            const int k = t + G * m;
+            const float2 cs = twr[k];
+            cf X1, X2;
+            untangle2x(reg[m], mir[-m * MSTRIDE], cs.x, cs.y, X1, X2);            // R_k, R_{NC-k}
+            const cf Y1 = mvdr_hermitian_bin(X1, k, g1, a.steer, half_inv_n);
+            const cf Y2 = mvdr_hermitian_bin(X2, NC - k, g1, a.steer, half_inv_n);
+            cf Zm;
+            retangle2x(Y1, Y2, cs.x, cs.y, reg[m], Zm);
+            mir[-m * MSTRIDE] = Zm;
+        }
+        group_sync<0>();
+#pragma unroll
+        for (int m = HM + 1; m < E; ++m) reg[m] = own[m * MSTRIDE];
+        {
+            const cf z8 = own[HM * MSTRIDE];
+            if (t != 0) reg[HM] = z8;
+        }
+        group_sync<0>();
+        group_fft<float, NC, E, true, 0>(reg, t, buf, tw);   // reg[m] = (y[2n], y[2n+1]), n = t + G*m
+        // ---- out[i] = (short)(w0 l[i] + y[511 + i]) (:189-191): output word j = (y[2n-1], y[2n]) with n = 256 + j, the odd
+        //      sample comes from the neighbouring lane
+        const long ob = b - a.skip_blocks;
+#pragma unroll
+        for (int m = HM; m < E; ++m) {
+            float yo = __shfl_up_sync(0xffffffffu, reg[m].y, 1);
+            const float yo31 = __shfl_sync(0xffffffffu, reg[m - 1].y, 31);
+            if (t == 0) yo = yo31;
+            if (ob >= 0) {
+                const int j = t + G * (m - HM);
+                const uint32_t wl = cl[j];
+                const float v0 = singular ? 0.f : fmaf(w0, s16lo(wl), yo), v1 = singular ? 0.f : fmaf(w0, s16hi(wl), reg[m].x);
+                reinterpret_cast<uint32_t *>(a.out + s * a.out_pitch + ob * B)[j] =
+                    ((uint32_t)(uint16_t)trunc16(v0)) | ((uint32_t)(uint16_t)trunc16(v1) << 16);
+                if (a.out_f32) *reinterpret_cast<float2 *>(a.out_f32 + s * a.f32_pitch + ob * B + 2 * j) = make_float2(v0, v1);
             }
         }
     }

@@ -131,6 +131,14 @@ static inline T __shfl_down_sync(unsigned, T v, unsigned d, int width = 32) {
     return jdsp_emul_shfl(v, src);
 }
 
+template <typename T>
+static inline T __shfl_up_sync(unsigned, T v, unsigned d, int width = 32) {
+    const int lane = jdsp_emul::S.cur & 31;
+    int src = lane - (int)d;
+    if (src < 0 || (src & ~(width - 1)) != (lane & ~(width - 1))) src = lane;
+    return jdsp_emul_shfl(v, src);
+}
+
 // math / conversion intrinsics used by the kernels
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline float __frcp_rn(float x) { return 1.0f / x; }

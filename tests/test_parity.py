@@ -487,11 +487,13 @@ def test_emulator_fiber_order_invariance(what, monkeypatch):
 MVDR_FLIPS = 2e-2
 
 
-@pytest.mark.parametrize("path", ["td", "fft"])
+@pytest.mark.parametrize("path", ["td", "fft", "fft-full"])
 def test_mvdr_reference_fixtures(be, monkeypatch, path):
     """Outputs of the unmodified program (tests/golden/make_golden.py): at most 1 LSB away, on a small share of samples;
     through the single-pass time-domain kernel (steering delay 0) and through the transform kernels."""
-    monkeypatch.setenv("JDSP_MVDR_PATH", path)
+    monkeypatch.setenv("JDSP_MVDR_PATH", path.split("-")[0])
+    if path == "fft-full":
+        monkeypatch.setenv("JDSP_MVDR_APPLY", "full")
     g = np.load(os.path.join(G, "mvdr.npz"))
     left, right = np.stack([g["left_3"], g["left_17"]]), np.stack([g["right_3"], g["right_17"]])
     out = be.ctx.mvdr(left, right, be.L.mvdr_params("ref"))
@@ -500,13 +502,15 @@ def test_mvdr_reference_fixtures(be, monkeypatch, path):
         assert_i16_parity(out[i], g[f"out_{stream}"], MVDR_FLIPS, f"mvdr fixture {stream}")
 
 
-@pytest.mark.parametrize("path", ["td", "fft"])
+@pytest.mark.parametrize("path", ["td", "fft", "fft-full"])
 def test_mvdr_dev_chunked_precast_and_edges(be, oracle, monkeypatch, path):
     """Device form: VAD decisions, the spatial matrix and the block count are exact; the pre-cast floats stay within 1e-4 of
     the peak of the oracle's doubles; feeding the stream in chunks changes nothing, bit for bit; streams that are all voice
     (matrix stays singular), silent on one microphone (singular) or silent on both emit zeros like the program; a steering
     delay != 0 exercises the per-bin phase and the program's in-place complex product."""
-    monkeypatch.setenv("JDSP_MVDR_PATH", path)
+    monkeypatch.setenv("JDSP_MVDR_PATH", path.split("-")[0])
+    if path == "fft-full":
+        monkeypatch.setenv("JDSP_MVDR_APPLY", "full")     # the two-microphone complex transform instead of the right-only packed one
     rng = np.random.default_rng(31)
     nb, B = 24, 512
     pairs = [synth.mvdr_pair(7, nb * B), synth.mvdr_pair(8, nb * B, delay=0, gain=1.0, sigma_r=50.0)]

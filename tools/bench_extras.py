@@ -231,23 +231,26 @@ if want("mvdr"):
         xr[s0:s0 + 256] = torch.clamp(torch.round(late), -32768, 32767).to(torch.int16)
         del late
     out = torch.empty((S, (nb - 1) * B), dtype=torch.int16, device=dev)
-    st = ctx.mvdr_state(p, S)
+    # delay 0 = the program's configuration (single-pass time-domain kernel); a steered beam takes the transform kernels
+    for name, dtime in (("mvdr", 0.0), ("mvdr_steered", 2.5e-4)):
+        p.dtime = dtime
+        st = ctx.mvdr_state(p, S)
 
-    def run_mvdr():
-        st.reset()
-        st.run(xl, xr, n, nb, out, (nb - 1) * B)
-    med, best = timed(run_mvdr, warm=2, reps=5)
-    alg = 2 * S * n * 2 + S * (nb - 1) * B * 2
-    torch.cuda.synchronize()
-    worst, flips, tot = 0, 0, 0
-    for s_ in (0, S // 2, S - 1):
-        ref = o.mvdr(xl[s_].cpu().numpy(), xr[s_].cpu().numpy())[0]
-        d = np.abs(out[s_].cpu().numpy().astype(int) - ref.astype(int))
-        worst, flips, tot = max(worst, int(d.max())), flips + int((d > 0).sum()), tot + d.size
-    emit({"config": "mvdr", "streams": S, "samples_per_microphone": n, "frames": S * nb, "ms": med, "msamples_s": S * n / med / 1e3,
-          "frames_per_s": S * nb / med * 1e3, "algorithmic_bytes": alg, "gbs": alg / med / 1e6, "frac_hbm": alg / med / 1e6 / PEAK,
-          "parity_i16_max_lsb": worst, "parity_flip_fraction": flips / tot})
-    st.close()
+        def run_mvdr():
+            st.reset()
+            st.run(xl, xr, n, nb, out, (nb - 1) * B)
+        med, best = timed(run_mvdr, warm=2, reps=5)
+        alg = 2 * S * n * 2 + S * (nb - 1) * B * 2
+        torch.cuda.synchronize()
+        worst, flips, tot = 0, 0, 0
+        for s_ in (0, S // 2, S - 1):
+            ref = o.mvdr(xl[s_].cpu().numpy(), xr[s_].cpu().numpy(), dtime)[0]
+            d = np.abs(out[s_].cpu().numpy().astype(int) - ref.astype(int))
+            worst, flips, tot = max(worst, int(d.max())), flips + int((d > 0).sum()), tot + d.size
+        emit({"config": name, "steering_delay_s": dtime, "streams": S, "samples_per_microphone": n, "frames": S * nb, "ms": med,
+              "msamples_s": S * n / med / 1e3, "frames_per_s": S * nb / med * 1e3, "algorithmic_bytes": alg, "gbs": alg / med / 1e6,
+              "frac_hbm": alg / med / 1e6 / PEAK, "parity_i16_max_lsb": worst, "parity_flip_fraction": flips / tot})
+        st.close()
     del xl, xr, out
 
 os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
