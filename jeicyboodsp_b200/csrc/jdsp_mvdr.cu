@@ -149,8 +149,14 @@ int jdsp_mvdr_i16_dev(jdsp_ctx *c, jdsp_mvdr_state *st, const int16_t *d_left, c
     a.voice = (uint8_t *)(a.er + items);
     a.vad_out = d_vad; a.n_streams = S; a.energy_thr = st->p.energy_thr; a.skip_blocks = skip;
     {   // VAD decisions and block energies, frame-parallel
-        auto kfn = mvdr_stats_kernel;
-        JDSP_LAUNCH_PTR(kfn, dim3(grid_for(c, ((long)items + 3) / 4, 16)), dim3(128), 0, c->stream, a);
+        const bool rows16 = in_pitch % 8 == 0 && (((uintptr_t)d_left | (uintptr_t)d_right) & 15) == 0;
+        if (rows16) {
+            auto kfn = mvdr_stats16_kernel;
+            JDSP_LAUNCH_PTR(kfn, dim3(grid_for(c, ((long)items + 3) / 4, 16)), dim3(128), 0, c->stream, a);
+        } else {
+            auto kfn = mvdr_stats_kernel;
+            JDSP_LAUNCH_PTR(kfn, dim3(grid_for(c, ((long)items + 3) / 4, 16)), dim3(128), 0, c->stream, a);
+        }
         TRY(launch_check(c));
     }
     {   // the program's sequential state machine, one thread per stream

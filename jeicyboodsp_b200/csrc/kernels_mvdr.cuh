@@ -388,6 +388,41 @@ JDSP_DEV uint4 mvdr_td_mix8(const uint4 &vl, const uint4 &vr, float w0, float g1
     return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+// The stats kernel of the transform path with the time-domain kernel's block code: 16-byte loads, lane-ordered window table in
+// shared memory, exponent-trick conversions, REDUX sums, energies only for non-voice blocks (the scan reads them only there).
+__global__ void __launch_bounds__(128) mvdr_stats16_kernel(MvdrArgs a) {
+    constexpr int B = MvdrGeom::B, N = MvdrGeom::N;
+    __shared__ __align__(16) double win_s[B];
+    for (int n = threadIdx.x; n < B; n += blockDim.x) win_s[(((n >> 8) * 4 + ((n >> 1) & 3)) * 32 + ((n >> 3) & 31)) * 2 + (n & 1)] = a.win_vad[n];
+    __syncthreads();
+    const int w = threadIdx.x / 32, t = threadIdx.x % 32;
+    const long n_items = a.n_streams * a.n_blocks;
+    StridedDivmod dm((long)blockIdx.x * 4 + w, (long)gridDim.x * 4, a.n_blocks);
+    for (long item = (long)blockIdx.x * 4 + w; item < n_items; item += (long)gridDim.x * 4, dm.next()) {
+        const long s = dm.q, b = dm.r;
+        const uint4 *pl = reinterpret_cast<const uint4 *>(a.l + s * a.in_pitch + b * B);
+        const uint4 l0 = pl[t], l1 = pl[32 + t];
+        unsigned long long ev = 0;
+        mvdr_td_vad8(l0, win_s + 2 * t, ev);
+        mvdr_td_vad8(l1, win_s + 256 + 2 * t, ev);
+        const long long evs = warp_sum_u40(ev);
+        const bool voice = (double)evs / (double)N > a.energy_thr;                            // :235-238
+        long long sls = 0, srs = 0;
+        if (!voice) {                                                                          // the right block is only read here
+            const uint4 *pr = reinterpret_cast<const uint4 *>(a.r + s * a.in_pitch + b * B);
+            const uint4 r0 = pr[t], r1 = pr[32 + t];
+            unsigned long long sl = 0, sr = 0;
+            mvdr_td_energy8(l0, sl); mvdr_td_energy8(l1, sl); mvdr_td_energy8(r0, sr); mvdr_td_energy8(r1, sr);
+            sls = warp_sum_u40(sl); srs = warp_sum_u40(sr);
+        }
+        if (t == 0) {
+            a.voice[item] = voice ? 1 : 0;
+            a.sl2[item] = sls; a.sr2[item] = srs;
+            if (a.vad_out) a.vad_out[item] = voice ? 1 : 0;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128, 7) mvdr_td_kernel(MvdrArgs a) {
     constexpr int B = MvdrGeom::B, N = MvdrGeom::N;
     // VAD window w[511 + n], stored in the order the lanes read it: sample n = 256 q + 8 t + 2 i + e sits at ((4 q + i) 32 + t) 2 + e

@@ -176,3 +176,24 @@ def test_mvdr_contract(be, oracle):
         d = np.abs(runs[0][s, :(nb - 1) * B].astype(int) - oracle.mvdr(*pairs[s])[0].astype(int))
         assert d.max() <= 1
     st.close()
+
+
+def test_mvdr_unaligned_rows_take_the_scalar_kernels(be, oracle):
+    """Rows that are only 4-byte aligned (input) / 2-byte aligned (output) fall back from the 16-byte-load kernels to the
+    scalar-load stats kernel and the two-microphone transform kernel: same decisions, samples within 1 LSB of the oracle."""
+    S, nb, B = 3, 10, 512
+    pairs = [synth.mvdr_pair(20 + s, nb * B) for s in range(S)]
+    pitch_in, pitch_out = nb * B + 2, (nb - 1) * B + 1
+    left, right = np.zeros((S, pitch_in), np.int16), np.zeros((S, pitch_in), np.int16)
+    for s in range(S):
+        left[s, :nb * B], right[s, :nb * B] = pairs[s]
+    st = be.ctx.mvdr_state(be.L.mvdr_params("ref"), S)
+    d_out, d_vad = be.zeros((S, pitch_out), np.int16), be.zeros((S, nb), np.uint8)
+    assert st.run(be.to_dev(left), be.to_dev(right), pitch_in, nb, d_out, pitch_out, None, 0, d_vad) == nb - 1
+    be.sync()
+    out, vad = be.to_host(d_out), be.to_host(d_vad)
+    for s in range(S):
+        o_out, _, _, o_vad = oracle.mvdr(*pairs[s])
+        assert np.array_equal(vad[s], o_vad)
+        assert np.abs(out[s, :(nb - 1) * B].astype(int) - o_out.astype(int)).max() <= 1
+    st.close()
