@@ -211,11 +211,13 @@ struct MfccGeom {
     static constexpr int NSLOT = NC / 2 + 1;
     static constexpr int SPT = (NSLOT + NT - 1) / NT;
     static constexpr int MAXMEL = 64, MAXCEP = 32;
+    static constexpr int MELP = MAXMEL + 4;          // pitch of a frame's mel row: the lanes of a warp store 8 frames x 4 channels at
+                                                     // once, 4 f + c' words apart mod 32 (a pitch of 64 was an 8-way conflict, ncu)
     static constexpr int FP = PADN + 1;              // frame pitch in complex slots: odd in 8-byte units mod 16, so the
                                                      // cross-frame reads of the mel stage hit different banks
     static constexpr size_t OFF_FBUF = 0;
     static constexpr size_t OFF_MEL = OFF_FBUF + ((((size_t)F * FP * sizeof(cf)) + 15) & ~(size_t)15);
-    static constexpr size_t OFF_DCT = OFF_MEL + (size_t)F * MAXMEL * sizeof(float);        // [n_mel][16] (cepstrum index fastest)
+    static constexpr size_t OFF_DCT = OFF_MEL + (size_t)F * MELP * sizeof(float);        // [n_mel][16] (cepstrum index fastest)
     static constexpr size_t OFF_START = OFF_DCT + (size_t)MAXMEL * 16 * sizeof(float);     // [MAXMEL+2]
     static constexpr size_t OFF_WINH = OFF_START + (size_t)(MAXMEL + 8) * sizeof(int);     // [N] half window (zero past frame_len)
     static constexpr size_t OFF_BAR = OFF_WINH + (size_t)N * sizeof(float);
@@ -231,7 +233,7 @@ template <int NC>
 __global__ void __launch_bounds__(MfccGeom<NC>::NT) mfcc_kernel(MfccArgs a) {
     using Geo = MfccGeom<NC>;
     constexpr int E = Geo::E, G = Geo::G, NT = Geo::NT, F = Geo::F, PADN = Geo::PADN, NSLOT = Geo::NSLOT, SPT = Geo::SPT;
-    constexpr int FP = Geo::FP, MAXMEL = Geo::MAXMEL, DP = 16;
+    constexpr int FP = Geo::FP, MELP = Geo::MELP, DP = 16;
     JDSP_DYN_SMEM(smem_raw);
     cf *fbuf = reinterpret_cast<cf *>(smem_raw + Geo::OFF_FBUF);
     float *mel = reinterpret_cast<float *>(smem_raw + Geo::OFF_MEL);
@@ -335,6 +337,8 @@ __global__ void __launch_bounds__(MfccGeom<NC>::NT) mfcc_kernel(MfccArgs a) {
         // the bins with index c+1.  Item = (channel, frame) with the frame fastest, so the lanes of a warp walk 4 neighbouring
         // channels of similar width.  (Measured and rejected: pairing channel p with C-1-p for equal work per thread and
         // splitting the walk into pad-free runs with four running sums -- 25 % SLOWER, the extra branches diverge.)
+        // (Also measured and rejected: two lanes per item, one per share lane, so that a warp's loads touch odd banks too --
+        // 2 % slower, the extra rounds cost more than the halved conflicts save.)
         for (int it = tid; it < C * F; it += NT) {
             const int c = it / F, f = it % F;
             const int i0 = mstart[c], i1 = mstart[c + 1], i2 = mstart[c + 2];
@@ -344,7 +348,7 @@ __global__ void __launch_bounds__(MfccGeom<NC>::NT) mfcc_kernel(MfccArgs a) {
             for (int i = i0; i < i1; ++i) acc += mg[pad16(i)].x;
 #pragma unroll 4
             for (int i = i1; i < i2; ++i) acc += mg[pad16(i)].y;
-            mel[f * MAXMEL + c] = logf(acc);  // :170-172
+            mel[f * MELP + c] = logf(acc);  // :170-172
         }
         __syncthreads();  // (E)
         // ---- M4 DCT (:176-183) with M5 lifter (:185-192) folded into the table ------------------------------
@@ -353,7 +357,7 @@ __global__ void __launch_bounds__(MfccGeom<NC>::NT) mfcc_kernel(MfccArgs a) {
         for (int it = tid; it < nf * DP; it += NT) {
             const int f = it / DP, i = it % DP;
             if (i >= NCEP) continue;
-            const float *ml = mel + f * MAXMEL;
+            const float *ml = mel + f * MELP;
             float acc = 0.f;
             float acc1 = 0.f;
             int c = 0;
