@@ -34,7 +34,12 @@ def test_exports_every_declared_symbol(lib):
 
 
 def test_struct_layouts_match_header(lib):
-    from jeicyboodsp_b200.binding import DenoiseParams, FastconvParams, MfccParams
+    from jeicyboodsp_b200.binding import DenoiseParams, FastconvParams, MfccParams, MvdrParams, PitchParams
+    assert C.sizeof(PitchParams) == 4 * 4 + 8
+    assert C.sizeof(MvdrParams) == 4 * 4 + 6 * 8
+    v = lib.mvdr_params("ref")         # BeamForming_MVDR_ver1.cpp:31-40,58-60
+    assert (v.n_fft, v.block, v.keep, v.energy_thr, v.fs, v.dtime, v.win_a0, v.win_a1, v.pi_literal) == \
+        (1024, 512, 511, 700.0, 16000.0, 0.0, 0.54, 0.46, 3.141592)
     assert C.sizeof(DenoiseParams) == 6 * 4 + 4 * 8
     assert C.sizeof(FastconvParams) == 6 * 4
     assert C.sizeof(MfccParams) == 6 * 4 + 5 * 8
