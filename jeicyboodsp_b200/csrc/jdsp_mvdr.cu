@@ -110,14 +110,19 @@ int jdsp_mvdr_i16_dev(jdsp_ctx *c, jdsp_mvdr_state *st, const int16_t *d_left, c
     // (two warps per SM and up) or the call is short; few long streams take the block-parallel transform path.
     // JDSP_MVDR_PATH=td|fft overrides the choice (tests run both).
     const bool aligned = in_pitch % 8 == 0 && out_pitch % 8 == 0 && (((uintptr_t)d_left | (uintptr_t)d_right | (uintptr_t)d_out) & 15) == 0;
+    // the 16-byte-load kernels keep the VAD energy in 32 bits by clamping |v| at `clamp` with clamp^2 > thr * N (see
+    // mvdr_td_vad8); that needs 512 clamp^2 < 2^32, i.e. thresholds below ~8000 (the program's is 700)
+    const double thr_n = st->p.energy_thr * (double)st->p.n_fft;
+    const unsigned vad_clamp = thr_n <= 0.0 ? 1u : (unsigned)floor(sqrt(thr_n)) + 1u;
+    const bool clamp_ok = thr_n < 8.0e6 && vad_clamp <= 2896u;
     const char *force = getenv("JDSP_MVDR_PATH");
     const bool want_td = force ? !strcmp(force, "td") : (S >= 2L * c->sm_count || n_blocks <= 8);
-    if (st->p.dtime == 0.0 && aligned && want_td) {
+    if (st->p.dtime == 0.0 && aligned && want_td && clamp_ok) {
         MvdrArgs a{};
         a.l = d_left; a.r = d_right; a.in_pitch = in_pitch; a.n_blocks = n_blocks;
         a.out = d_out; a.out_pitch = out_pitch; a.out_f32 = d_out_f32; a.f32_pitch = f32_pitch;
         a.win_vad = st->d_win; a.st_iter = st->d_iter; a.st_pl = st->d_pl; a.st_pr = st->d_pr; a.st_el = st->d_el; a.st_er = st->d_er;
-        a.vad_out = d_vad; a.n_streams = S; a.energy_thr = st->p.energy_thr; a.skip_blocks = skip;
+        a.vad_out = d_vad; a.n_streams = S; a.energy_thr = st->p.energy_thr; a.skip_blocks = skip; a.vad_clamp = vad_clamp;
         auto kfn = mvdr_td_kernel;
         JDSP_LAUNCH_PTR(kfn, dim3(grid_for(c, (S + 3) / 4, 16)), dim3(128), 0, c->stream, a);
         TRY(launch_check(c));
@@ -150,7 +155,8 @@ int jdsp_mvdr_i16_dev(jdsp_ctx *c, jdsp_mvdr_state *st, const int16_t *d_left, c
     a.vad_out = d_vad; a.n_streams = S; a.energy_thr = st->p.energy_thr; a.skip_blocks = skip;
     {   // VAD decisions and block energies, frame-parallel
         const bool rows16 = in_pitch % 8 == 0 && (((uintptr_t)d_left | (uintptr_t)d_right) & 15) == 0;
-        if (rows16) {
+        a.vad_clamp = vad_clamp;
+        if (rows16 && clamp_ok) {
             auto kfn = mvdr_stats16_kernel;
             JDSP_LAUNCH_PTR(kfn, dim3(grid_for(c, ((long)items + 3) / 4, 16)), dim3(128), 0, c->stream, a);
         } else {

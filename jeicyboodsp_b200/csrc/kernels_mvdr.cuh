@@ -47,6 +47,7 @@ struct MvdrArgs {
     uint8_t *voice; long long *sl2, *sr2;   // [stream][n_blocks]
     double *el, *er;                         // [stream][n_blocks] matrix in force for each block
     uint8_t *vad_out;                        // nullable [stream][n_blocks]
+    unsigned vad_clamp;            // 16-byte-load kernels: |v| is clamped here before squaring (see mvdr_td_vad8); clamp^2 > thr * N
     long n_streams;
     double energy_thr;
     long skip_blocks;              // 1 when the state has seen no block yet (:202-205)
@@ -58,6 +59,16 @@ struct MvdrGeom {
     static constexpr size_t SMEM = (size_t)WARPS * PADN * sizeof(cf);
     static_assert(G == 32, "one warp per frame pair");
 };
+
+// w = R^-1 c / (c^H R^-1 c) for R = diag(EL, ER): |w0| = ER / (EL + ER), |w1| = EL / (EL + ER); a singular matrix (no estimate
+// yet, or a silent microphone) is the program's NaN -> (short) 0: both weights 0 and the caller writes zeros.
+JDSP_DEV bool mvdr_weights(double el, double er, float &w0, float &g1) {
+    const bool singular = !(el > 0.0) || !(er > 0.0);
+    const double inv = 1.0 / (el + er);
+    w0 = singular ? 0.f : (float)(er * inv);
+    g1 = singular ? 0.f : (float)(el * inv);
+    return singular;
+}
 
 JDSP_DEV long long warp_sum_i64(long long v) {
 #pragma unroll
@@ -147,8 +158,8 @@ __global__ void __launch_bounds__(MvdrGeom::NT, 4) mvdr_apply_kernel(MvdrArgs a)
         group_sync<0>();
         // ---- weights of this block (:144-152 in closed form for a diagonal matrix) ------------------------------------------
         const double el = a.el[item], er = a.er[item];
-        const bool singular = !(el > 0.0) || !(er > 0.0);
-        const float w0 = singular ? 0.f : (float)(er / (el + er)), g1 = singular ? 0.f : (float)(el / (el + er));
+        float w0, g1;
+        const bool singular = mvdr_weights(el, er, w0, g1);
 #pragma unroll
         for (int m = 0; m < E; ++m) {
             const int i = t + G * m;
@@ -260,8 +271,8 @@ __global__ void __launch_bounds__(MvdrRGeom::NT) mvdr_apply_r_kernel(MvdrArgs a)
         if (t == 0) buf[Geo::PADN] = reg[0];
         // ---- weights of this block (:144-152 in closed form for a diagonal matrix)
         const double el = a.el[item], er = a.er[item];
-        const bool singular = !(el > 0.0) || !(er > 0.0);
-        const float w0 = singular ? 0.f : (float)(er / (el + er)), g1 = singular ? 0.f : (float)(el / (el + er));
+        float w0, g1;
+        const bool singular = mvdr_weights(el, er, w0, g1);
         {   // bin NC/2 = 256 (thread 0, m = 8) pairs with itself: R = 2 conj(A), Z' = 2 conj(Y)
             const cf R = cmake<float>(2.f * reg[HM].x, -2.f * reg[HM].y);
             const cf Y = mvdr_hermitian_bin(R, NC / 2, g1, a.steer, half_inv_n);
@@ -353,17 +364,19 @@ JDSP_DEV double2 lds_f64x2(const double *p) {
 #ifndef JDSP_MVDR_LAZY
 #define JDSP_MVDR_LAZY 1       // 1: block energies only for non-voice blocks (the only ones the spatial matrix uses, :95-105)
 #endif
-// VAD energy of 8 left samples (one 16-byte word): sum of (short)(x * w)^2 (:224-228)
-JDSP_DEV void mvdr_td_vad8(const uint4 &vl, const double *w, unsigned long long &ev) {
+// VAD energy of 8 left samples (one 16-byte word): sum of (short)(x * w)^2 (:224-228).  The decision is sum > thr * N, so
+// a single |v| with v^2 > thr * N already settles it: |v| is clamped to `clamp` (clamp^2 > thr * N, 512 clamp^2 < 2^32, set by
+// the host), which leaves the decision exact and lets the whole sum, warp reduction included, live in 32 bits.
+JDSP_DEV void mvdr_td_vad8(const uint4 &vl, const double *w, unsigned clamp, unsigned &ev) {
     const unsigned wl[4] = {vl.x, vl.y, vl.z, vl.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const double2 ww = lds_f64x2(w + 64 * i);            // [word][lane] pairs: consecutive lanes read consecutive 16 bytes
         const int l0 = (int)(int16_t)(wl[i] & 0xffffu), l1 = (int)wl[i] >> 16;
         // the square only needs |trunc(x w)| = trunc(|x| w)
-        const unsigned v0 = (unsigned)__double2int_rz(u16_to_f64((unsigned)abs(l0)) * ww.x);
-        const unsigned v1 = (unsigned)__double2int_rz(u16_to_f64((unsigned)abs(l1)) * ww.y);
-        ev += (unsigned long long)(v0 * v0) + (unsigned long long)(v1 * v1);                   // :228, each square < 2^31
+        const unsigned v0 = min((unsigned)__double2int_rz(u16_to_f64((unsigned)abs(l0)) * ww.x), clamp);
+        const unsigned v1 = min((unsigned)__double2int_rz(u16_to_f64((unsigned)abs(l1)) * ww.y), clamp);
+        ev += v0 * v0 + v1 * v1;                                                               // :228
     }
 }
 // sum of squares of 8 samples
@@ -402,10 +415,10 @@ __global__ void __launch_bounds__(128) mvdr_stats16_kernel(MvdrArgs a) {
         const long s = dm.q, b = dm.r;
         const uint4 *pl = reinterpret_cast<const uint4 *>(a.l + s * a.in_pitch + b * B);
         const uint4 l0 = pl[t], l1 = pl[32 + t];
-        unsigned long long ev = 0;
-        mvdr_td_vad8(l0, win_s + 2 * t, ev);
-        mvdr_td_vad8(l1, win_s + 256 + 2 * t, ev);
-        const long long evs = warp_sum_u40(ev);
+        unsigned ev = 0;
+        mvdr_td_vad8(l0, win_s + 2 * t, a.vad_clamp, ev);
+        mvdr_td_vad8(l1, win_s + 256 + 2 * t, a.vad_clamp, ev);
+        const unsigned evs = warp_sum_u32(ev);
         const bool voice = (double)evs / (double)N > a.energy_thr;                            // :235-238
         long long sls = 0, srs = 0;
         if (!voice) {                                                                          // the right block is only read here
@@ -438,15 +451,17 @@ __global__ void __launch_bounds__(128, 7) mvdr_td_kernel(MvdrArgs a) {
         long long pl = a.st_pl[s], pr = a.st_pr[s];
         double el = a.st_el[s], er = a.st_er[s];
         const long nb = a.n_blocks;
+        float w0, g1;                                          // weights: recomputed only when the matrix changes
+        mvdr_weights(el, er, w0, g1);                          // singular <=> both are 0
         MvdrBlockRegs cur = mvdr_load_block(l, r, t);
         for (long b = 0; b < nb; ++b) {
             const long bn = b + 1 < nb ? b + 1 : b;           // the next block is in flight while this one is processed
             const MvdrBlockRegs nxt = mvdr_load_block(l + bn * B, r + bn * B, t);
             // ---- VAD on the left block (:209-243) and the block energies
-            unsigned long long ev = 0;
-            mvdr_td_vad8(cur.l0, win_s + 2 * t, ev);
-            mvdr_td_vad8(cur.l1, win_s + 256 + 2 * t, ev);
-            const long long evs = warp_sum_u40(ev);
+            unsigned ev = 0;
+            mvdr_td_vad8(cur.l0, win_s + 2 * t, a.vad_clamp, ev);
+            mvdr_td_vad8(cur.l1, win_s + 256 + 2 * t, a.vad_clamp, ev);
+            const unsigned evs = warp_sum_u32(ev);
             const bool voice = (double)evs / (double)N > a.energy_thr;                        // :235-238
 #if !JDSP_MVDR_LAZY
             unsigned long long sl = 0, sr = 0;
@@ -461,7 +476,7 @@ __global__ void __launch_bounds__(128, 7) mvdr_td_kernel(MvdrArgs a) {
                 const long long sls = warp_sum_u40(sl), srs = warp_sum_u40(sr);
 #endif
                 ++iter;
-                if (iter > 1) { el += (double)(pl + sls); er += (double)(pr + srs); }
+                if (iter > 1) { el += (double)(pl + sls); er += (double)(pr + srs); mvdr_weights(el, er, w0, g1); }
                 pl = sls; pr = srs;
             } else {
                 iter = 0;
@@ -470,8 +485,6 @@ __global__ void __launch_bounds__(128, 7) mvdr_td_kernel(MvdrArgs a) {
             // ---- ProcessMVDR with bin-independent real weights
             const long ob = b - a.skip_blocks;
             if (ob >= 0) {
-                const bool singular = !(el > 0.0) || !(er > 0.0);
-                const float w0 = singular ? 0.f : (float)(er / (el + er)), g1 = singular ? 0.f : (float)(el / (el + er));
                 uint4 *po = reinterpret_cast<uint4 *>(a.out + s * a.out_pitch + ob * B);
                 if (a.out_f32) {
                     float y[16];

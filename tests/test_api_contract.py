@@ -197,3 +197,32 @@ def test_mvdr_unaligned_rows_take_the_scalar_kernels(be, oracle):
         assert np.array_equal(vad[s], o_vad)
         assert np.abs(out[s, :(nb - 1) * B].astype(int) - o_out.astype(int)).max() <= 1
     st.close()
+
+
+@pytest.mark.parametrize("thr", [-1.0, 0.0, 40.0, 700.0, 5000.0, 20000.0])
+def test_mvdr_vad_threshold_sweep_clamped_energy_is_exact(be, thr):
+    """The 16-byte-load kernels keep the VAD energy in 32 bits by clamping |v| above sqrt(thr N); the scalar-load kernel sums
+    in 64 bits.  Both must take identical decisions for any threshold (beyond ~8000 the library itself falls back to 64 bits),
+    on quiet, loud and full-scale input."""
+    rng = np.random.default_rng(int(abs(thr)) + 5)
+    nb, B = 16, 512
+    sig = [rng.normal(0, a, nb * B) for a in (3.0, 30.0, 300.0, 3000.0)] + [32767.0 * np.sign(rng.normal(0, 1, nb * B)), np.zeros(nb * B)]
+    left = np.stack([np.clip(np.round(x), -32768, 32767).astype(np.int16) for x in sig])
+    right = left[::-1].copy()
+    S = left.shape[0]
+    p = be.L.mvdr_params("ref")
+    p.energy_thr = thr
+    vads = []
+    for pad in (0, 2):                      # pad 2: rows only 4-byte aligned -> scalar-load stats kernel with 64-bit sums
+        pitch = nb * B + pad
+        l2, r2 = np.zeros((S, pitch), np.int16), np.zeros((S, pitch), np.int16)
+        l2[:, :nb * B], r2[:, :nb * B] = left, right
+        st = be.ctx.mvdr_state(p, S)
+        d_out, d_vad = be.zeros((S, nb * B), np.int16), be.zeros((S, nb), np.uint8)
+        assert st.run(be.to_dev(l2), be.to_dev(r2), pitch, nb, d_out, nb * B, None, 0, d_vad) == nb - 1
+        be.sync()
+        vads.append(be.to_host(d_vad).copy())
+        st.close()
+    assert np.array_equal(vads[0], vads[1])
+    if 0.0 < thr < 5000.0:
+        assert vads[0].any() and not vads[0].all()      # the sweep really crosses the threshold
