@@ -1,6 +1,7 @@
 // jdsp_api.cu -- C ABI (include/jdsp.h), part 1: context, memory helpers and the FFT entry points.  Compiled by nvcc for
 // sm_100a into jeicyboodsp_b200/libjdsp.so together with jdsp_stft.cu and jdsp_conv_mfcc.cu.  (tests/emul compiles the same
 // files with g++ -DJDSP_EMUL against a CPU execution emulator to debug index logic without a GPU; that build is test-only.)
+#include <algorithm>
 #include "jdsp_host.hpp"
 #include "kernels_fft.cuh"
 
@@ -124,6 +125,20 @@ static int launch_c2c_big(jdsp_ctx *c, const cx<float> *in, cx<float> *out, long
     return launch_check(c);
 }
 
+template <int M, bool INV>
+static int launch_c2c_split2(jdsp_ctx *c, const cx<float> *in, cx<float> *out, long batch) {
+    using Geo = FftBigGeom<M>;
+    void *t32, *twN;
+    TRY(get_table(c, 6, M, &t32));
+    TRY(get_table(c, 3, 2 * M, &twN));
+    auto kfn = fft_c2c_split2_kernel<M, INV>;
+    TRY(opt_in_smem(kfn, Geo::SMEM));
+    // an even grid keeps the two halves of a transform on CTAs that run at the same time
+    const unsigned grid = (unsigned)std::max<long>(2, std::min<long>(2 * batch, (long)(c->sm_count & ~1)));
+    JDSP_LAUNCH_PTR(kfn, dim3(grid), dim3(Geo::THREADS), Geo::SMEM, c->stream, in, out, batch, (const cx<float> *)t32, (const cx<float> *)twN, 1.0f);
+    return launch_check(c);
+}
+
 template <typename T, int N1, int N2, bool INV>
 static int launch_c2c_fourstep(jdsp_ctx *c, const cx<T> *in, cx<T> *out, long batch, int tkind) {
     // 256-thread CTAs (3 per SM at 80 registers): the four barriers of a tile stall 8 warps instead of 16 and more tiles
@@ -221,6 +236,7 @@ static int fft_dispatch(jdsp_ctx *c, const cx<T> *in, cx<T> *out, int n, long ba
             if constexpr (sizeof(T) == 4) { if (getenv("JDSP_FFT_FUSED")) return launch_c2c_fused<64, 256, INV>(c, in, out, batch); }
             return launch_c2c_fourstep<T, 64, 256, INV>(c, in, out, batch, tkind);
         case 32768:
+            if constexpr (sizeof(T) == 4) { if (!getenv("JDSP_FFT_NO_SPLIT") && !getenv("JDSP_FFT_FUSED")) return launch_c2c_split2<16384, INV>(c, (const cx<float> *)in, (cx<float> *)out, batch); }
             if constexpr (sizeof(T) == 4) { if (getenv("JDSP_FFT_FUSED")) return launch_c2c_fused<128, 256, INV>(c, in, out, batch); }
             return launch_c2c_fourstep<T, 128, 256, INV>(c, in, out, batch, tkind);
         case 65536:

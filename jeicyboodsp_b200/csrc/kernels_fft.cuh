@@ -209,6 +209,63 @@ fft_c2c_big_kernel(const cx<float> *__restrict__ in, cx<float> *__restrict__ out
     }
 }
 
+// ---- N = 2 M with M = 16384 on chip: one radix-2 decimation-in-frequency step folded into the LOAD of the on-chip kernel.
+//   y_r[n] = (x[n] + (-1)^r x[n + M]) W_N^(n r),  n < M, r = 0, 1;     X[2 k + r] = DFT_M(y_r)[k].
+// Work item = (transform, r); the two items of a transform run on neighbouring CTAs at the same time, so the input is read
+// from HBM once (the sibling's read is an L2 hit) and the interleaved halves of the output rows meet in L2 before they are
+// written back: one HBM round trip instead of the four-step's two.  W_N^n = W_N^t (one table load per thread) times
+// W_N^(G m) (a 32-entry broadcast), so no 128 KB twiddle stream per item.
+template <int M, bool INV>
+__global__ void __launch_bounds__(FftBigGeom<M>::THREADS, 1)
+fft_c2c_split2_kernel(const cx<float> *__restrict__ in, cx<float> *__restrict__ out, long batch, const cx<float> *__restrict__ tw,
+                      const cx<float> *__restrict__ twN, float scale) {
+    using Geo = FftBigGeom<M>;
+    constexpr int E = Geo::E, G = Geo::G, N = 2 * M;
+    JDSP_DYN_SMEM(smem_raw);
+    cx<float> *exch = reinterpret_cast<cx<float> *>(smem_raw);
+    const int t = threadIdx.x;
+    const cx<float> wt = twN[t];                                  // W_N^t
+    for (long i = blockIdx.x; i < 2 * batch; i += gridDim.x) {
+        const long f = i >> 1;
+        const int r = (int)(i & 1);
+        cx<float> reg[E];
+        const cx<float> *src = in + f * N + t;
+#pragma unroll
+        for (int m = 0; m < E; ++m) reg[m] = src[G * m];
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+            const cx<float> hi = src[M + G * m];
+            if (r == 0) {
+                reg[m] = cadd(reg[m], hi);
+            } else {
+                const cx<float> d = csub(reg[m], hi);
+                const cx<float> w = cmul<false>(wt, twN[G * m]);   // W_N^(t + G m); the second factor is the same for the whole CTA
+                reg[m] = cmul<INV>(d, w);
+            }
+        }
+        __syncthreads();   // the previous item is done with the exchange buffer
+        {   // pull this CTA's next item into L2 (the half this r reads first; the sibling pulls the other half)
+            const long in2 = i + gridDim.x;
+            if (in2 < 2 * batch) {
+                const char *nx = reinterpret_cast<const char *>(in + (in2 >> 1) * N + (in2 & 1) * M);
+#pragma unroll
+                for (int k = 0; k < (int)(M * sizeof(cx<float>) / 128 / G); ++k) prefetch_l2(nx + ((long)t + (long)G * k) * 128);
+            }
+        }
+        const cx<float> *twp = tw;
+#ifndef JDSP_EMUL
+        asm volatile("" : "+l"(twp)::"memory");
+#endif
+        group_fft<float, M, E, INV, 1>(reg, t, exch, twp);
+        cx<float> *dst = out + f * N + r + 2 * t;
+#pragma unroll
+        for (int m = 0; m < E; ++m) { reg[m].x *= scale; reg[m].y *= scale; dst[2 * G * m] = reg[m]; }
+#ifndef JDSP_EMUL
+        asm volatile("" ::: "memory");
+#endif
+    }
+}
+
 // ---- four-step for N = N1 * N2 (both handled by one thread group each) -----------------------------------
 // Step A: for CT adjacent columns n2, DFT over n1 (stride N2), multiply by W_N^(n2*k1), write row-major [k1][n2].
 // Global accesses are CT*sizeof(cx) contiguous bytes per row; all loads of a tile are issued before the first
