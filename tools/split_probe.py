@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.ins
 import numpy as np, torch
 from jeicyboodsp_b200.binding import Context, Library
 PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6454.6
-L = Library(); ctx = Context(L, 0, stream=torch.cuda.current_stream().cuda_stream)
+L = Library(sys.argv[1] if len(sys.argv) > 1 else None); ctx = Context(L, 0, stream=torch.cuda.current_stream().cuda_stream)
 total = 1 << 29
 xy = torch.empty(2 * total, dtype=torch.complex64, device="cuda"); x, y = xy[:total], xy[total:]
 torch.view_as_real(x).uniform_(-1, 1)
