@@ -182,7 +182,7 @@ int jdsp_mvdr_i16_dev(jdsp_ctx *c, jdsp_mvdr_state *st, const int16_t *d_left, c
         auto kfn = mvdr_apply_r_kernel;
         TRY(opt_in_smem(kfn, MvdrRGeom::SMEM));
         CU(cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        JDSP_LAUNCH_PTR(kfn, dim3(grid_for(c, ((long)items + MvdrRGeom::WARPS - 1) / MvdrRGeom::WARPS, 6)), dim3(MvdrRGeom::NT), MvdrRGeom::SMEM,
+        JDSP_LAUNCH_PTR(kfn, dim3(grid_for(c, ((long)items + MvdrRGeom::WARPS - 1) / MvdrRGeom::WARPS, JDSP_MVDR_AR_CTAS)), dim3(MvdrRGeom::NT), MvdrRGeom::SMEM,
                         c->stream, a);
         TRY(launch_check(c));
     } else {

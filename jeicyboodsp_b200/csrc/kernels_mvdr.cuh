@@ -225,7 +225,10 @@ JDSP_DEV cf mvdr_hermitian_bin(cf R, int i, float g1, const float2 *steer, float
     return cmake<float>((A.x + Bq.x) * half_inv_n, (A.y - Bq.y) * half_inv_n);
 }
 
-__global__ void __launch_bounds__(MvdrRGeom::NT) mvdr_apply_r_kernel(MvdrArgs a) {
+#ifndef JDSP_MVDR_AR_CTAS
+#define JDSP_MVDR_AR_CTAS 7    // resident CTAs per SM the register budget is capped for (72 registers, no spills; 6: +2.4 % time, 8: spills)
+#endif
+__global__ void __launch_bounds__(MvdrRGeom::NT, JDSP_MVDR_AR_CTAS) mvdr_apply_r_kernel(MvdrArgs a) {
     using Geo = MvdrRGeom;
     constexpr int NC = Geo::NC, N = Geo::N, B = Geo::B, E = Geo::E, G = Geo::G, HM = E / 2, NT = Geo::NT;
     constexpr int MSTRIDE = G + G / 16;
