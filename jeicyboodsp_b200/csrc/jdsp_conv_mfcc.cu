@@ -1,6 +1,7 @@
 // jdsp_conv_mfcc.cu -- C ABI (include/jdsp.h), part 3: the fast-convolution and MFCC pipelines.
 #include "jdsp_host.hpp"
 #include "kernels_conv_mfcc.cuh"
+#include "kernels_mfcc.cuh"
 
 // ---------------------------------------------------------------------------------------------------
 // Fast convolution
@@ -182,8 +183,12 @@ struct jdsp_mfcc_plan {
     jdsp_mfcc_params p;
     std::vector<double> weight;  // rgdFilterBank
     std::vector<int32_t> chan;   // rgdFiBins
-    float *d_win_half = nullptr, *d_mel_w = nullptr, *d_dct = nullptr;
-    int *d_mel_start = nullptr;
+    // device tables of mfcc_kernel (kernels_mfcc.cuh): window, DCT x lifter, and the filterbank laid out per thread slot
+    float *d_win_half = nullptr, *d_dct = nullptr;
+    float2 *d_slot_w = nullptr;
+    uint32_t *d_slot_ctl = nullptr;
+    int *d_slot_pid = nullptr, *d_run_start = nullptr;
+    int n_pieces = 0;
 };
 
 extern "C" {
@@ -206,7 +211,8 @@ int jdsp_mfcc_plan_destroy(jdsp_ctx *c, jdsp_mfcc_plan *pl) {
     if (!pl) return JDSP_OK;
     REQUIRE(c, "ctx is null");
     cudaStreamSynchronize(c->stream);
-    cudaFree(pl->d_win_half); cudaFree(pl->d_mel_w); cudaFree(pl->d_dct); cudaFree(pl->d_mel_start);
+    cudaFree(pl->d_win_half); cudaFree(pl->d_dct); cudaFree(pl->d_slot_w); cudaFree(pl->d_slot_ctl); cudaFree(pl->d_slot_pid);
+    cudaFree(pl->d_run_start);
     delete pl;
     return JDSP_OK;
 }
@@ -237,10 +243,39 @@ int jdsp_mfcc_plan_create(jdsp_ctx *c, const jdsp_mfcc_params *p, jdsp_mfcc_plan
         if (w < 0) w = 0;
         pl->weight[i] = w;
     }
-    std::vector<float> mw(nbin);
-    for (int i = 0; i < nbin; ++i) mw[i] = (float)pl->weight[i];
-    std::vector<int> start((size_t)C + 2);
-    for (int v = 0; v <= C + 1; ++v) { int i = 0; while (i < nbin && pl->chan[i] < v) ++i; start[v] = i; }
+    // The kernel's view of the filterbank.  Thread t of a frame group (G = nbin/16 threads) holds the contiguous bins
+    // 8t..8t+7 (low chain, ascending; the last thread also bin nbin/2) and nbin-8t..nbin-8t-7 (high chain, descending; "bin
+    // nbin" of thread 0 does not exist).  A piece = a maximal run of bins of one thread range with the same channel index;
+    // pieces are numbered in bin order, so the pieces of one index are consecutive and run_start[c] finds them.
+    const int G = nbin / 16, KP = 8, NSLOT = 2 * KP + 1;
+    std::vector<int> range(nbin), piece(nbin);
+    for (int i = 0; i < nbin; ++i) range[i] = i <= nbin / 2 ? (i == nbin / 2 ? G - 1 : i / KP) : G + (nbin - i) / KP;
+    for (int i = 0, id = -1; i < nbin; ++i) {
+        if (i == 0 || range[i] != range[i - 1] || pl->chan[i] != pl->chan[i - 1]) ++id;
+        piece[i] = id;
+    }
+    pl->n_pieces = piece[nbin - 1] + 1;
+    std::vector<float2> slot_w((size_t)NSLOT * G, make_float2(0.f, 0.f));
+    std::vector<uint32_t> slot_ctl((size_t)G, 0u);
+    std::vector<int> slot_pid((size_t)2 * G, 0), run_start((size_t)C + 3, pl->n_pieces);
+    auto share = [&](int i) { return make_float2((float)(1.0 - pl->weight[i]), (float)pl->weight[i]); };
+    for (int t = 0; t < G; ++t) {
+        for (int j = 0; j < KP; ++j) {
+            const int lo = KP * t + j, hi = nbin - KP * t - j;
+            slot_w[(size_t)j * G + t] = share(lo);
+            if (j > 0 && piece[lo] != piece[lo - 1]) slot_ctl[t] |= 1u << j;
+            if (hi < nbin) {
+                slot_w[(size_t)(KP + 1 + j) * G + t] = share(hi);
+                if (j > 0 && hi + 1 < nbin && piece[hi] != piece[hi + 1]) slot_ctl[t] |= 1u << (16 + j);
+            }
+        }
+        slot_pid[t] = piece[KP * t];
+        slot_pid[G + t] = piece[nbin - KP * t < nbin ? nbin - KP * t : nbin - 1];
+    }
+    slot_w[(size_t)KP * G + (G - 1)] = share(nbin / 2);
+    if (piece[nbin / 2] != piece[nbin / 2 - 1]) slot_ctl[G - 1] |= 1u << KP;
+    for (int i = nbin - 1; i >= 0; --i) run_start[pl->chan[i]] = piece[i];   // first piece of every index that occurs ...
+    for (int v = C + 1; v >= 0; --v) if (run_start[v] > run_start[v + 1]) run_start[v] = run_start[v + 1];   // ... the next one's otherwise
     // M4 DCT (:176-183) times M5 lifter (:185-192)
     std::vector<float> dct((size_t)p->n_cep * C);
     for (int i = 1; i <= p->n_cep; ++i) {
@@ -250,9 +285,11 @@ int jdsp_mfcc_plan_create(jdsp_ctx *c, const jdsp_mfcc_params *p, jdsp_mfcc_plan
     std::vector<float> wh(W);
     for (int i = 0; i < W; ++i) wh[i] = (float)(0.5 * (p->win_a0 - p->win_a1 * cos(2 * p->pi_literal * i / (W - 1))));
     TRY(upload(c, wh, &pl->d_win_half));
-    TRY(upload(c, mw, &pl->d_mel_w));
     TRY(upload(c, dct, &pl->d_dct));
-    TRY(upload(c, start, &pl->d_mel_start));
+    TRY(upload(c, slot_w, &pl->d_slot_w));
+    TRY(upload(c, slot_ctl, &pl->d_slot_ctl));
+    TRY(upload(c, slot_pid, &pl->d_slot_pid));
+    TRY(upload(c, run_start, &pl->d_run_start));
     *out = pl;
     return JDSP_OK;
 }
@@ -264,13 +301,17 @@ int jdsp_mfcc_plan_tables(jdsp_mfcc_plan *pl, double *weight, int32_t *chan) {
 }
 }  // extern "C"
 
-template <int NC> static int launch_mfcc(jdsp_ctx *c, const MfccArgs &a) {
+template <int NC, int MU> static int launch_mfcc(jdsp_ctx *c, const MfccArgs &a) {
     using Geo = MfccGeom<NC>;
-    auto kfn = mfcc_kernel<NC>;
-    const size_t smem = Geo::smem(a.frame_len, a.hop);
-    TRY(opt_in_smem(kfn, smem));
-    const long tiles = a.n_utts * ((a.n_frames + Geo::F - 1) / Geo::F);
-    JDSP_LAUNCH_PTR(kfn, dim3(grid_for(c, tiles, 32)), dim3(Geo::NT), smem, c->stream, a);
+    auto kfn = mfcc_kernel<NC, MU>;
+    TRY(opt_in_smem(kfn, Geo::SMEM));
+    int per_sm = 4;
+#ifndef JDSP_EMUL
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, Geo::NT, Geo::SMEM));
+    if (per_sm < 1) return fail(JDSP_ERR_CUDA, "MFCC kernel does not fit an SM");
+#endif
+    const long items = a.n_utts * ((a.n_frames + Geo::FPW - 1) / Geo::FPW);
+    JDSP_LAUNCH_PTR(kfn, dim3(grid_for(c, (items + Geo::NW - 1) / Geo::NW, per_sm)), dim3(Geo::NT), Geo::SMEM, c->stream, a);
     return launch_check(c);
 }
 
@@ -291,11 +332,14 @@ int jdsp_mfcc_frames_i16_dev(jdsp_ctx *c, jdsp_mfcc_plan *pl, const int16_t *d_i
     TRY(get_table(c, 0, NC, &tw));
     TRY(get_table(c, 2, NC, &twr));
     MfccArgs a;
-    a.in = d_in; a.in_pitch = in_pitch; a.n_utts = n_utts; a.n_samples = n_samples; a.n_frames = nf;
+    a.in = d_in; a.in_pitch = in_pitch; a.n_utts = n_utts; a.n_frames = nf;
     a.feat = d_feat; a.feat_pitch = feat_pitch; a.win_half = pl->d_win_half; a.tw = (const cf *)tw; a.twr = (const float2 *)twr;
-    a.mel_w = pl->d_mel_w; a.mel_start = pl->d_mel_start; a.dct = pl->d_dct;
+    a.slot_w = pl->d_slot_w; a.slot_ctl = pl->d_slot_ctl; a.slot_pid = pl->d_slot_pid; a.run_start = pl->d_run_start; a.dct = pl->d_dct;
     a.frame_len = p.frame_len; a.hop = p.hop; a.n_mel = p.n_mel; a.n_cep = p.n_cep; a.preemph = (float)p.preemph;
-    return NC == 256 ? launch_mfcc<256>(c, a) : launch_mfcc<512>(c, a);
+    // packed points t + G*m, m >= MU, lie past frame_len for every thread: the 13-row instance covers frames of up to 13*n_fft/32
+    // samples (the bench preset's 400 of 512)
+    if (NC == 256) return p.frame_len <= 13 * 32 ? launch_mfcc<256, 13>(c, a) : launch_mfcc<256, 16>(c, a);
+    return launch_mfcc<512, 16>(c, a);
 }
 
 int jdsp_mfcc_program_i16(jdsp_ctx *c, const jdsp_mfcc_params *p, const int16_t *pcm, long n_samples, double *rows, long *n_rows) {

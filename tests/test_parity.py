@@ -388,6 +388,24 @@ def test_mfcc_tables_bit_exact(be, oracle):
         plan.close()
 
 
+@pytest.mark.parametrize("preset", ["bench", "mid", "ref"])
+def test_mfcc_generalised_framing_ragged(be, oracle, preset):
+    """Frame counts that do not fill the last warp step, more warp steps than resident warps on the GPU (staging buffers
+    and mbarrier phases are reused), one utterance only one frame long."""
+    p = be.L.mfcc_params(preset)
+    op = OMP.preset(preset)
+    plan = be.ctx.mfcc_plan(p)
+    for U, nfr in ((1, 1), (2, 5), ((700 if be.name == "gpu" else 2), (37 if be.name == "gpu" else 3))):
+        n = p.frame_len + (nfr - 1) * p.hop + 8          # 8 samples that belong to no frame
+        x = np.stack([synth.mfcc_utterance(u, n) for u in range(U)])
+        d_feat = be.zeros((U, nfr, p.n_cep), np.float32)
+        assert plan.run(be.to_dev(x), n, U, n, d_feat, nfr * p.n_cep) == nfr
+        feat = be.to_host(d_feat)
+        for u in sorted({0, U // 2, U - 1}):
+            assert_float_parity(feat[u], oracle.mfcc_frames(x[u], op), f"mfcc {preset} U={U}")
+    plan.close()
+
+
 def test_mfcc_bench_framing(be, oracle):
     p = be.L.mfcc_params("bench")
     n = 16000 if be.name == "emul" else 160000
@@ -449,7 +467,8 @@ def test_pitch_dev_chunked_and_edge_inputs(be, oracle):
     st.close()
 
 
-@pytest.mark.parametrize("what", ["denoise_tile", "denoise_stream", "denoise_stream_ref", "pitch", "mvdr_td", "mvdr_fft", "fft4096"])
+@pytest.mark.parametrize("what", ["denoise_tile", "denoise_stream", "denoise_stream_ref", "pitch", "mvdr_td", "mvdr_fft", "fft4096",
+                                  "mfcc_bench", "mfcc_ref"])
 def test_emulator_fiber_order_invariance(what, monkeypatch):
     """Missing-barrier detector for the emulated build: ascending and descending fiber schedules must agree."""
     from backends import EmulBackend
@@ -462,6 +481,16 @@ def test_emulator_fiber_order_invariance(what, monkeypatch):
     elif what == "pitch":
         x = np.stack([synth.denoise_stream(s, 9 * 512) for s in range(3)])
         run = lambda: np.concatenate([a.astype(np.float64) for a in be.ctx.pitch(x, be.L.pitch_params("ref"))], axis=1)
+    elif what.startswith("mfcc"):
+        p = be.L.mfcc_params(what[5:])
+        n = p.frame_len + 6 * p.hop          # 7 frames: an odd count leaves the last warp step half empty at n_fft 512
+        x = np.stack([synth.mfcc_utterance(u, n) for u in range(3)])
+        def run():
+            plan = be.ctx.mfcc_plan(p)
+            out = np.zeros((3, 7, p.n_cep), np.float32)
+            assert plan.run(x, n, 3, n, out, 7 * p.n_cep) == 7
+            plan.close()
+            return out
     elif what.startswith("mvdr"):
         monkeypatch.setenv("JDSP_MVDR_PATH", what[5:])
         lr = [synth.mvdr_pair(s, 9 * 512) for s in range(3)]
