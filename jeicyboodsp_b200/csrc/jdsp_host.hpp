@@ -69,6 +69,7 @@ template <typename T> static int upload(jdsp_ctx *c, const std::vector<T> &h, T 
 template <typename T> static std::vector<cx<T>> pass_twiddles(int n, int emax = 16) {
     const int E = n < emax ? n : emax;
     std::vector<cx<T>> h;
+    if (!is_pow2(n)) return h;   // callers validate; a non power of two would stall the loop below (n / ns floors to 1)
     for (int ns = 1; ns < n;) {
         const int r = (n / ns) < E ? (n / ns) : E;
         if (ns > 1)
@@ -88,6 +89,7 @@ template <typename T> static std::vector<cx<T>> pass_twiddles(int n, int emax = 
 // kind 3/4: float/double flat exp(-2*pi*j*q/n), q<n (four-step inter-stage twiddle)
 // kind 5: float pass twiddles for length n with 8 points per thread     kind 6: with 32 points per thread
 static int get_table(jdsp_ctx *c, int kind, int n, void **out) {
+    if (!is_pow2(n)) return fail(JDSP_ERR_UNSUPPORTED, "transform lengths must be powers of two");   // pass_twiddles would never finish
     auto key = std::make_pair(kind, n);
     auto it = c->tables.find(key);
     if (it != c->tables.end()) { *out = it->second; return JDSP_OK; }
@@ -140,23 +142,76 @@ static unsigned grid_for(jdsp_ctx *c, long tiles, int per_sm) {
 }
 
 static int ensure_workspace(jdsp_ctx *c, size_t in_bytes, size_t out_bytes, int nslots) {
-    if (c->ws_in_bytes < in_bytes || c->ws_out_bytes < out_bytes || (nslots > 1 && !c->ws_in[1])) {
-        CU(cudaStreamSynchronize(c->stream));
-        for (int i = 0; i < 3; ++i) {
-            if (c->pipe[i]) CU(cudaStreamSynchronize(c->pipe[i]));
-            cudaFree(c->ws_in[i]); cudaFree(c->ws_out[i]);
-            c->ws_in[i] = c->ws_out[i] = nullptr;
-        }
-        c->ws_in_bytes = in_bytes > c->ws_in_bytes ? in_bytes : c->ws_in_bytes;
-        c->ws_out_bytes = out_bytes > c->ws_out_bytes ? out_bytes : c->ws_out_bytes;
-        for (int i = 0; i < 3; ++i) {
-            CU(cudaMalloc(&c->ws_in[i], c->ws_in_bytes));
-            CU(cudaMalloc(&c->ws_out[i], c->ws_out_bytes));
-        }
-    }
     for (int i = 0; i < 3; ++i)
         if (!c->pipe[i]) CU(cudaStreamCreateWithFlags(&c->pipe[i], cudaStreamNonBlocking));
+    if (c->ws_in_bytes >= in_bytes && c->ws_out_bytes >= out_bytes && c->ws_in[0] && (nslots <= 1 || c->ws_in[2])) return JDSP_OK;
+    CU(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 3; ++i) CU(cudaStreamSynchronize(c->pipe[i]));
+    const size_t nin = in_bytes > c->ws_in_bytes ? in_bytes : c->ws_in_bytes, nout = out_bytes > c->ws_out_bytes ? out_bytes : c->ws_out_bytes;
+    // the old buffers go first (two generations of a 3 x 2 x 256 MB workspace need not coexist); sizes and pointers are
+    // committed only once all six new buffers exist, so a failure leaves an empty, consistent workspace behind
+    for (int i = 0; i < 3; ++i) { cudaFree(c->ws_in[i]); cudaFree(c->ws_out[i]); c->ws_in[i] = c->ws_out[i] = nullptr; }
+    c->ws_in_bytes = c->ws_out_bytes = 0;
+    void *ni[3] = {nullptr, nullptr, nullptr}, *no[3] = {nullptr, nullptr, nullptr};
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 3 && e == cudaSuccess; ++i) {
+        e = cudaMalloc(&ni[i], nin ? nin : 16);
+        if (e == cudaSuccess) e = cudaMalloc(&no[i], nout ? nout : 16);
+    }
+    if (e != cudaSuccess) {
+        for (int i = 0; i < 3; ++i) { cudaFree(ni[i]); cudaFree(no[i]); }
+        return fail(JDSP_ERR_CUDA, std::string("workspace allocation: ") + cudaGetErrorString(e));
+    }
+    for (int i = 0; i < 3; ++i) { c->ws_in[i] = ni[i]; c->ws_out[i] = no[i]; }
+    c->ws_in_bytes = nin; c->ws_out_bytes = nout;
     return JDSP_OK;
+}
+
+// Host-buffer forms: rows (streams, sources, utterances, transforms) travel through the device in chunks over the three pipe
+// streams, so the host-to-device copy of chunk i+1, the kernels of chunk i and the device-to-host copy of chunk i-1 overlap.
+//   in / out        host buffers (pinned for full copy rate), row pitches in bytes, `in_copy` / `out_copy` bytes used per row
+//   d_in_row / d_out_row   bytes per row of the device staging buffers (>= the copied bytes; the launcher may pad rows)
+//   launch(u0, nu, d_in, d_out)  enqueues the kernels for rows [u0, u0 + nu) on c->stream (which is the chunk's pipe stream
+//                                for the duration of the call)
+template <class Launch>
+static int pipe_rows(jdsp_ctx *c, long n_rows, const void *in, size_t in_pitch, size_t in_copy, size_t d_in_row, void *out, size_t out_pitch,
+                     size_t out_copy, size_t d_out_row, Launch launch, size_t chunk_bytes = (size_t)128 << 20) {
+    if (n_rows <= 0) return JDSP_OK;
+    const size_t row = d_in_row > d_out_row ? d_in_row : d_out_row;
+    long chunk = (long)(chunk_bytes / (row ? row : 1));
+    if (chunk < 1) chunk = 1;
+    if (chunk > n_rows) chunk = n_rows;
+    const int nslots = (n_rows + chunk - 1) / chunk > 1 ? 3 : 1;
+    TRY(ensure_workspace(c, (size_t)chunk * d_in_row, (size_t)chunk * d_out_row, nslots));
+    CU(cudaStreamSynchronize(c->stream));   // whatever the caller enqueued (state resets, table uploads) is done before the pipe streams start
+    int rc = JDSP_OK, slot = 0;
+    cudaStream_t saved = c->stream;
+    for (long u0 = 0; u0 < n_rows && rc == JDSP_OK; u0 += chunk, slot = (slot + 1) % nslots) {
+        const long nu = n_rows - u0 < chunk ? n_rows - u0 : chunk;
+        cudaStream_t q = c->pipe[slot];
+        cudaError_t e = cudaSuccess;
+        const char *src = (const char *)in + (size_t)u0 * in_pitch;
+        if (in_copy > 0) {
+            if (in_pitch == in_copy && d_in_row == in_copy) e = cudaMemcpyAsync(c->ws_in[slot], src, (size_t)nu * in_copy, cudaMemcpyHostToDevice, q);
+            else e = cudaMemcpy2DAsync(c->ws_in[slot], d_in_row, src, in_pitch, in_copy, (size_t)nu, cudaMemcpyHostToDevice, q);
+        }
+        if (e != cudaSuccess) { rc = fail(JDSP_ERR_CUDA, std::string("host form H2D: ") + cudaGetErrorString(e)); break; }
+        c->stream = q;
+        rc = launch(u0, nu, c->ws_in[slot], c->ws_out[slot]);
+        c->stream = saved;
+        if (rc != JDSP_OK) break;
+        char *dst = (char *)out + (size_t)u0 * out_pitch;
+        if (out_copy > 0) {
+            if (out_pitch == out_copy && d_out_row == out_copy) e = cudaMemcpyAsync(dst, c->ws_out[slot], (size_t)nu * out_copy, cudaMemcpyDeviceToHost, q);
+            else e = cudaMemcpy2DAsync(dst, out_pitch, c->ws_out[slot], d_out_row, out_copy, (size_t)nu, cudaMemcpyDeviceToHost, q);
+        }
+        if (e != cudaSuccess) { rc = fail(JDSP_ERR_CUDA, std::string("host form D2H: ") + cudaGetErrorString(e)); break; }
+    }
+    for (int i = 0; i < 3; ++i) {
+        cudaError_t e = cudaStreamSynchronize(c->pipe[i]);
+        if (e != cudaSuccess && rc == JDSP_OK) rc = fail(JDSP_ERR_CUDA, std::string("host form: ") + cudaGetErrorString(e));
+    }
+    return rc;
 }
 
 // copy the previous block's tail into the unread part of a short final block (the reference's fread

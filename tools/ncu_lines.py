@@ -30,7 +30,7 @@ for ln in dis.splitlines():
         amap[int(m.group(1), 16)] = (line, m.group(2).strip())
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
-cur, hdr, per_line, per_op, tot_i, tot_s = None, None, {}, {}, 0.0, 0.0
+cur, hdr, per_line, per_op, tot_i, tot_s, tot_w = None, None, {}, {}, 0.0, 0.0, 0.0
 first_addr = None
 nk = 0
 for r in rows:
@@ -47,14 +47,15 @@ for r in rows:
     a = a - first_addr
     ie = float(r[hdr.index("Instructions Executed")] or 0)
     sm = float(r[hdr.index("# Samples")] or 0)
-    tot_i += ie; tot_s += sm
+    wf = float(r[hdr.index("L1 Wavefronts Shared")] or 0) if "L1 Wavefronts Shared" in hdr else 0.0
+    tot_i += ie; tot_s += sm; tot_w += wf
     base = min(amap) if amap else 0
     key, op = amap.get(a, amap.get(a - 0, ((None, 0), r[1])))
-    per_line.setdefault(key, [0.0, 0.0]); per_line[key][0] += ie; per_line[key][1] += sm
+    per_line.setdefault(key, [0.0, 0.0, 0.0]); per_line[key][0] += ie; per_line[key][1] += sm; per_line[key][2] += wf
     opn = r[1].split()[0] if not r[1].startswith("@") else r[1].split()[1]
     opn = opn.split(".")[0] + ("." + opn.split(".")[1] if opn.startswith(("LDS", "STS", "LDG", "STG")) and "." in opn else "")
-    per_op.setdefault(opn, [0.0, 0.0]); per_op[opn][0] += ie; per_op[opn][1] += sm
-print(f"total warp-instr {tot_i:.0f}, samples {tot_s:.0f}")
+    per_op.setdefault(opn, [0.0, 0.0, 0.0]); per_op[opn][0] += ie; per_op[opn][1] += sm; per_op[opn][2] += wf
+print(f"total warp-instr {tot_i:.0f}, samples {tot_s:.0f}, shared wavefronts {tot_w:.0f}")
 src_cache = {}
 def src(key):
     if not key or not key[0]: return "?"
@@ -65,8 +66,8 @@ def src(key):
     t = src_cache[f]
     return f"{f}:{l}  " + (t[l - 1].strip()[:100] if 0 < l <= len(t) else "")
 print("--- by source line")
-for key, (ie, sm) in sorted(per_line.items(), key=lambda kv: -kv[1][0])[:top]:
-    print(f"{ie / tot_i * 100:5.1f}% inst {sm / max(tot_s, 1) * 100:5.1f}% samples | {src(key)}")
+for key, (ie, sm, wf) in sorted(per_line.items(), key=lambda kv: -kv[1][0])[:top]:
+    print(f"{ie / tot_i * 100:5.1f}% inst {sm / max(tot_s, 1) * 100:5.1f}% samples {wf / max(tot_w, 1) * 100:5.1f}% smem-wf | {src(key)}")
 print("--- by opcode")
-for op, (ie, sm) in sorted(per_op.items(), key=lambda kv: -kv[1][0])[:30]:
-    print(f"{ie / tot_i * 100:5.1f}% inst {sm / max(tot_s, 1) * 100:5.1f}% samples | {op}")
+for op, (ie, sm, wf) in sorted(per_op.items(), key=lambda kv: -kv[1][0])[:30]:
+    print(f"{ie / tot_i * 100:5.1f}% inst {sm / max(tot_s, 1) * 100:5.1f}% samples {wf / max(tot_w, 1) * 100:5.1f}% smem-wf | {op}")
