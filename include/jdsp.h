@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define JDSP_ABI_VERSION 3
+#define JDSP_ABI_VERSION 4
 
 #define JDSP_OK 0
 #define JDSP_ERR_INVALID (-1)     /* bad argument */
@@ -78,6 +78,9 @@ int jdsp_fft_process(jdsp_ctx *ctx, const jdsp_complex64 *in, jdsp_complex64 *ou
 /* device-resident batched transforms (config 5, the size sweep) */
 int jdsp_fft_c2c_f32(jdsp_ctx *ctx, const jdsp_complex32 *d_in, jdsp_complex32 *d_out, int n, long batch, int forward);
 int jdsp_fft_c2c_f64(jdsp_ctx *ctx, const jdsp_complex64 *d_in, jdsp_complex64 *d_out, int n, long batch, int forward);
+/* the fp32 batched transform on HOST buffers ({re,im} floats, `batch` transforms back to back; pinned memory for full copy
+ * rate): copies and kernels are pipelined over chunks of transforms */
+int jdsp_fft_c2c_f32_host(jdsp_ctx *ctx, const jdsp_complex32 *in, jdsp_complex32 *out, int n, long batch, int forward);
 /* The permutation Bitrev builds (FFTAlgorithm_ver2.cpp:186-207), widened to 32 bit so it is valid for
  * every n (the reference's `short` table breaks at 2^16).  The Stockham kernels never apply it; it is
  * exported because "bit-reversal must be bit-exact" is part of the parity contract. */
@@ -91,6 +94,10 @@ int jdsp_roundtrip_i16_dev(jdsp_ctx *ctx, const int16_t *d_in, long in_pitch, in
 /* Host form mirroring the program on one stream: `pcm` is the data after the 44-byte header (:59);
  * a short final block keeps the previous block's tail (:64); out gets ceil(n/n_fft)*n_fft samples. */
 int jdsp_roundtrip_i16(jdsp_ctx *ctx, const int16_t *pcm, long n_samples, int n_fft, int16_t *out, long *n_out);
+/* the same for n_streams signals at once (rows of n_samples at in_pitch; out rows of ceil(n/n_fft)*n_fft at out_pitch),
+ * copies and kernels pipelined over chunks of streams */
+int jdsp_roundtrip_batch_i16(jdsp_ctx *ctx, const int16_t *in, long in_pitch, long n_streams, long n_samples, int n_fft,
+                             int16_t *out, long out_pitch, long *n_out);
 
 /* ---- D1-D5: VAD-gated noise estimate + spectral subtraction / Wiener -------------------------------- */
 #define JDSP_DENOISE_SS 0     /* SpectralSubtraction()  SpectralSubtraction_final.cpp:201-264 */
@@ -130,7 +137,7 @@ int jdsp_denoise_i16_dev(jdsp_ctx *ctx, jdsp_denoise_state *st, const int16_t *d
                          long *n_out_blocks);
 /* Host form: n_streams whole streams of n_samples each (these two programs skip no header, :89-90);
  * stale-tail rule on a short final block; out rows get (ceil(n/hop)-2)*hop samples.  Copies are
- * pipelined with compute over chunks of streams. */
+ * pipelined with compute over chunks of TIME (every chunk carries all streams; the stream state links the chunks). */
 int jdsp_denoise_i16(jdsp_ctx *ctx, const jdsp_denoise_params *p, const int16_t *in, long in_pitch, long n_streams,
                      long n_samples, int16_t *out, long out_pitch, long *n_out_samples);
 /* number of noise-spectrum publishes so far per stream (host array of n_streams) -- harness check
@@ -236,6 +243,11 @@ int jdsp_fastconv_i16_dev(jdsp_ctx *ctx, jdsp_fastconv_state *st, const int16_t 
 int jdsp_fastconv_mix_i16_dev(jdsp_ctx *ctx, jdsp_fastconv_state *st, int sources_per_scene, const int16_t *d_in,
                               long in_pitch, long n_blocks, int16_t *d_out, long out_pitch, float *d_out_f32,
                               long f32_pitch, long *n_out_blocks);
+/* Host form of the call above: in [source][n_samples] (pitch in_pitch) and out [source][ear][emitted*block] (ear pitch out_pitch)
+ * are HOST buffers; a short final block follows the stale-tail rule; copies and kernels are pipelined over chunks of sources.
+ * *n_out_samples (nullable) = emitted*block. */
+int jdsp_fastconv_i16_host(jdsp_ctx *ctx, jdsp_fastconv_state *st, const int16_t *in, long in_pitch, long n_samples,
+                           int16_t *out, long out_pitch, long *n_out_samples);
 /* Host form mirroring the program on one source: pcm after the 44-byte header (:79), stale tail,
  * out [ear][(ceil(n/block)-history)*block]. */
 int jdsp_fastconv_i16(jdsp_ctx *ctx, const jdsp_fastconv_params *p, const double *taps, const int16_t *pcm,
@@ -268,6 +280,9 @@ int jdsp_mfcc_plan_tables(jdsp_mfcc_plan *plan, double *weight, int32_t *chan);
  *   *n_frames (nullable, host) = (n_samples - frame_len)/hop + 1. */
 int jdsp_mfcc_frames_i16_dev(jdsp_ctx *ctx, jdsp_mfcc_plan *plan, const int16_t *d_in, long in_pitch, long n_utts,
                              long n_samples, float *d_feat, long feat_pitch, long *n_frames);
+/* The same on HOST buffers (in [utt][n_samples], feat [utt][n_frames][n_cep]), pipelined over chunks of utterances. */
+int jdsp_mfcc_frames_i16(jdsp_ctx *ctx, jdsp_mfcc_plan *plan, const int16_t *in, long in_pitch, long n_utts, long n_samples,
+                         float *feat, long feat_pitch, long *n_frames);
 /* Host form mirroring the program on one file (requires frame_len == n_fft == 2*hop): pcm after the 44-byte
  * header (:84), blocks of 2*hop with the stale-tail rule, the framer sees [hop zeros | blocks], the very
  * first row is dropped (:95-97); rows are widened to the `.mfc` format, raw double[n_cep] (:99). */

@@ -74,7 +74,8 @@ ABI_SYMBOLS = [
     "jdsp_abi_version", "jdsp_last_error", "jdsp_device_count", "jdsp_create", "jdsp_create_on_stream",
     "jdsp_destroy", "jdsp_sync", "jdsp_cuda_stream", "jdsp_kernel_launches", "jdsp_malloc", "jdsp_free",
     "jdsp_host_alloc", "jdsp_host_free", "jdsp_memcpy_h2d", "jdsp_memcpy_d2h", "jdsp_fft_process",
-    "jdsp_fft_c2c_f32", "jdsp_fft_c2c_f64", "jdsp_bitrev_table", "jdsp_roundtrip_i16_dev", "jdsp_roundtrip_i16",
+    "jdsp_fft_c2c_f32", "jdsp_fft_c2c_f32_host", "jdsp_fft_c2c_f64", "jdsp_bitrev_table", "jdsp_roundtrip_i16_dev", "jdsp_roundtrip_i16",
+    "jdsp_roundtrip_batch_i16", "jdsp_fastconv_i16_host", "jdsp_mfcc_frames_i16",
     "jdsp_denoise_params_preset", "jdsp_denoise_state_create", "jdsp_denoise_state_reset",
     "jdsp_denoise_state_destroy", "jdsp_denoise_i16_dev", "jdsp_denoise_i16", "jdsp_denoise_publish_counts",
     "jdsp_fastconv_params_preset", "jdsp_fastconv_state_create", "jdsp_fastconv_state_reset",
@@ -188,6 +189,11 @@ class Context:
         self.L.check(self.lib.jdsp_fft_c2c_f32(self.h, _ptr(d_in), _ptr(d_out), C.c_int(n), C.c_long(batch),
                                                C.c_int(1 if forward else 0)))
 
+    def fft_c2c_f32_host(self, h_in, h_out, n: int, batch: int, forward: bool) -> None:
+        """complex64 host buffers (numpy or pinned torch), `batch` transforms back to back."""
+        self.L.check(self.lib.jdsp_fft_c2c_f32_host(self.h, _ptr(h_in), _ptr(h_out), C.c_int(n), C.c_long(batch),
+                                                    C.c_int(1 if forward else 0)))
+
     def fft_c2c_f64(self, d_in, d_out, n: int, batch: int, forward: bool) -> None:
         self.L.check(self.lib.jdsp_fft_c2c_f64(self.h, _ptr(d_in), _ptr(d_out), C.c_int(n), C.c_long(batch),
                                                C.c_int(1 if forward else 0)))
@@ -206,6 +212,13 @@ class Context:
         self.L.check(self.lib.jdsp_roundtrip_i16(self.h, _ptr(pcm), C.c_long(len(pcm)), C.c_int(n_fft), _ptr(out),
                                                  C.byref(n_out)))
         return out[: n_out.value]
+
+    def roundtrip_batch_raw(self, h_in, in_pitch, n_streams, n_samples, n_fft, h_out, out_pitch) -> int:
+        """Host form on many streams: int16 host rows in, ceil(n/n_fft)*n_fft samples per row out."""
+        got = C.c_long(0)
+        self.L.check(self.lib.jdsp_roundtrip_batch_i16(self.h, _ptr(h_in), C.c_long(in_pitch), C.c_long(n_streams), C.c_long(n_samples),
+                                                       C.c_int(n_fft), _ptr(h_out), C.c_long(out_pitch), C.byref(got)))
+        return got.value
 
     # ---- denoise ----------------------------------------------------------------------------------------
     def denoise_state(self, params: DenoiseParams, n_streams: int) -> "DenoiseState":
@@ -394,6 +407,13 @@ class FastconvState:
             self.ctx.lib.jdsp_fastconv_state_destroy(self.ctx.h, self.h)
             self.h = C.c_void_p(0)
 
+    def run_host(self, h_in, in_pitch, n_samples, h_out, out_pitch) -> int:
+        """Host form: int16 [n_sources][n_samples] in, int16 [n_sources][n_ears][emitted*block] out (ear pitch out_pitch)."""
+        got = C.c_long(0)
+        self.ctx.L.check(self.ctx.lib.jdsp_fastconv_i16_host(self.ctx.h, self.h, _ptr(h_in), C.c_long(in_pitch), C.c_long(n_samples),
+                                                             _ptr(h_out), C.c_long(out_pitch), C.byref(got)))
+        return got.value
+
     def run(self, d_in, in_pitch, n_blocks, d_out, out_pitch, d_f32=None, f32_pitch=0, sources_per_scene: int = 1) -> int:
         got = C.c_long(0)
         if sources_per_scene == 1:
@@ -429,6 +449,12 @@ class MfccPlan:
     def n_frames(self, n_samples: int) -> int:
         p = self.params
         return (n_samples - p.frame_len) // p.hop + 1 if n_samples >= p.frame_len else 0
+
+    def run_host(self, h_in, in_pitch, n_utts, n_samples, h_feat, feat_pitch) -> int:
+        got = C.c_long(0)
+        self.ctx.L.check(self.ctx.lib.jdsp_mfcc_frames_i16(self.ctx.h, self.h, _ptr(h_in), C.c_long(in_pitch), C.c_long(n_utts),
+                                                           C.c_long(n_samples), _ptr(h_feat), C.c_long(feat_pitch), C.byref(got)))
+        return got.value
 
     def run(self, d_in, in_pitch, n_utts, n_samples, d_feat, feat_pitch) -> int:
         got = C.c_long(0)

@@ -33,7 +33,8 @@ static int create_common(int device, cudaStream_t borrowed, bool borrow, jdsp_ct
     if (borrow) {
         c->stream = borrowed;
     } else {
-        CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete c; return fail(JDSP_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
         c->own_stream = true;
     }
     int sms = 0;
@@ -53,6 +54,7 @@ int jdsp_destroy(jdsp_ctx *c) {
     for (int i = 0; i < 3; ++i) { cudaFree(c->ws_in[i]); cudaFree(c->ws_out[i]); }
     for (auto *st : c->denoise_cache) jdsp_denoise_state_destroy(c, st);
     for (auto &p : c->pipe) if (p) cudaStreamDestroy(p);
+    for (auto &ev : c->pipe_ev) if (ev) cudaEventDestroy(ev);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return JDSP_OK;
@@ -257,6 +259,17 @@ int jdsp_fft_c2c_f32(jdsp_ctx *c, const jdsp_complex32 *d_in, jdsp_complex32 *d_
     return forward ? fft_dispatch<float, false>(c, (const cx<float> *)d_in, (cx<float> *)d_out, n, batch)
                    : fft_dispatch<float, true>(c, (const cx<float> *)d_in, (cx<float> *)d_out, n, batch);
 }
+int jdsp_fft_c2c_f32_host(jdsp_ctx *c, const jdsp_complex32 *in, jdsp_complex32 *out, int n, long batch, int forward) {
+    REQUIRE(c && in && out, "null argument");
+    REQUIRE(is_pow2(n) && n >= 2 && n <= 65536, "n must be a power of two in [2, 65536]");
+    REQUIRE(batch >= 0, "negative batch");
+    if (batch == 0) return JDSP_OK;
+    CU(cudaSetDevice(c->device));
+    const size_t row = (size_t)n * sizeof(jdsp_complex32);
+    return pipe_rows(c, batch, in, row, row, row, out, row, row, row, [&](long, long nb, void *d_in, void *d_out) {
+        return jdsp_fft_c2c_f32(c, (const jdsp_complex32 *)d_in, (jdsp_complex32 *)d_out, n, nb, forward);
+    });
+}
 int jdsp_fft_c2c_f64(jdsp_ctx *c, const jdsp_complex64 *d_in, jdsp_complex64 *d_out, int n, long batch, int forward) {
     REQUIRE(c && d_in && d_out, "null argument");
     REQUIRE(is_pow2(n) && n >= 2, "n must be a power of two >= 2");
@@ -274,7 +287,7 @@ int jdsp_fft_process(jdsp_ctx *c, const jdsp_complex64 *in, jdsp_complex64 *out,
     const size_t bytes = (size_t)batch * n * sizeof(jdsp_complex64);
     jdsp_complex64 *d_in = nullptr, *d_out = nullptr;
     CU(cudaMalloc((void **)&d_in, bytes));
-    CU(cudaMalloc((void **)&d_out, bytes));
+    if (cudaMalloc((void **)&d_out, bytes) != cudaSuccess) { cudaFree(d_in); return fail(JDSP_ERR_CUDA, "fft_process: device allocation failed"); }
     int rc = JDSP_OK;
     do {
         if (cudaMemcpyAsync(d_in, in, bytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { rc = fail(JDSP_ERR_CUDA, "H2D copy failed"); break; }

@@ -67,7 +67,8 @@ int jdsp_fastconv_state_create(jdsp_ctx *c, const jdsp_fastconv_params *p, long 
     memset(hin.data(), 0, hin.size() * sizeof(jdsp_complex64));
     for (long f = 0; f < nfilt * p->n_ears; ++f)
         for (int i = 0; i < p->n_taps && i < N; ++i) hin[f * N + i].re = taps[f * p->n_taps + i];
-    TRY(jdsp_fft_process(c, hin.data(), hout.data(), (int)N, 1, nfilt * p->n_ears));
+    int rc = jdsp_fft_process(c, hin.data(), hout.data(), (int)N, 1, nfilt * p->n_ears);
+    if (rc != JDSP_OK) { delete st; return rc; }
     std::vector<cf> hs((size_t)nfilt * p->n_ears * (NC + 1));
     const double sc = 1.0 / (2.0 * (double)N);
     for (long f = 0; f < nfilt * p->n_ears; ++f)
@@ -75,9 +76,11 @@ int jdsp_fastconv_state_create(jdsp_ctx *c, const jdsp_fastconv_params *p, long 
             hs[f * (NC + 1) + k].x = (float)(hout[f * N + k].re * sc);
             hs[f * (NC + 1) + k].y = (float)(hout[f * N + k].im * sc);
         }
-    TRY(upload(c, hs, &st->d_hs));
-    CU(cudaMalloc((void **)&st->d_hist, (size_t)n_sources * p->history_blocks * p->block * sizeof(int16_t)));
-    TRY(jdsp_fastconv_state_reset(c, st));
+    rc = upload(c, hs, &st->d_hs);
+    if (rc == JDSP_OK && cudaMalloc((void **)&st->d_hist, (size_t)n_sources * p->history_blocks * p->block * sizeof(int16_t)) != cudaSuccess)
+        rc = fail(JDSP_ERR_CUDA, "fast-conv history allocation failed");
+    if (rc == JDSP_OK) rc = jdsp_fastconv_state_reset(c, st);
+    if (rc != JDSP_OK) { jdsp_fastconv_state_destroy(c, st); return rc; }
     *out = st;
     return JDSP_OK;
 }
@@ -92,11 +95,15 @@ template <int NC, int Q> static int launch_fastconv(jdsp_ctx *c, const FastconvA
     JDSP_LAUNCH_PTR(kfn, dim3(grid_for(c, a.n_scenes, 32)), dim3(Geo::NT), smem, c->stream, a);
     return launch_check(c);
 }
+// src0 / nsrc: the slice of the state's sources this launch covers (the host form walks the sources in chunks and advances the
+// block counter itself once every chunk has been through: `advance` false)
 static int fastconv_run(jdsp_ctx *c, jdsp_fastconv_state *st, int sources_per_scene, const int16_t *d_in, long in_pitch, long n_blocks,
-                        int16_t *d_out, long out_pitch, float *d_out_f32, long f32_pitch, long *n_out_blocks) {
+                        int16_t *d_out, long out_pitch, float *d_out_f32, long f32_pitch, long *n_out_blocks, long src0 = 0, long nsrc = -1,
+                        bool advance = true) {
     REQUIRE(c && st && d_in, "null argument");
     REQUIRE(n_blocks >= 0, "negative n_blocks");
-    REQUIRE(sources_per_scene >= 1 && st->n_sources % sources_per_scene == 0, "sources_per_scene must divide n_sources");
+    if (nsrc < 0) nsrc = st->n_sources;
+    REQUIRE(sources_per_scene >= 1 && nsrc % sources_per_scene == 0 && src0 % sources_per_scene == 0, "sources_per_scene must divide n_sources");
     const jdsp_fastconv_params &p = st->p;
     const long skip = st->seen < p.history_blocks ? p.history_blocks - st->seen : 0;
     const long emitted = n_blocks > skip ? n_blocks - skip : 0;
@@ -112,8 +119,9 @@ static int fastconv_run(jdsp_ctx *c, jdsp_fastconv_state *st, int sources_per_sc
     TRY(get_table(c, 2, NC, &twr));
     FastconvArgs a;
     a.in = d_in; a.in_pitch = in_pitch; a.n_blocks = n_blocks; a.out = d_out; a.out_pitch = out_pitch;
-    a.out_f32 = d_out_f32; a.f32_pitch = f32_pitch; a.hs = st->d_hs; a.tw = (const cf *)tw; a.twr = (const float2 *)twr;
-    a.st_hist = st->d_hist; a.n_scenes = st->n_sources / sources_per_scene; a.sources_per_scene = sources_per_scene;
+    a.out_f32 = d_out_f32; a.f32_pitch = f32_pitch; a.tw = (const cf *)tw; a.twr = (const float2 *)twr;
+    a.hs = p.shared_filter ? st->d_hs : st->d_hs + src0 * (long)p.n_ears * (NC + 1);
+    a.st_hist = st->d_hist + src0 * (long)p.history_blocks * p.block; a.n_scenes = nsrc / sources_per_scene; a.sources_per_scene = sources_per_scene;
     a.B = p.block; a.q = p.history_blocks; a.n_ears = p.n_ears; a.shared_filter = p.shared_filter; a.seen0 = st->seen;
     int rc;
     const int key = NC * 16 + p.history_blocks;
@@ -128,7 +136,7 @@ static int fastconv_run(jdsp_ctx *c, jdsp_fastconv_state *st, int sources_per_sc
         case 4096 * 16 + 7: rc = launch_fastconv<4096, 7>(c, a); break;  // the reference program's literal constants
         default: return fail(JDSP_ERR_UNSUPPORTED, "fast-conv supports history_blocks 1 (n_fft 512..4096), 3 (2048, 4096) or 7 (4096, 8192)");
     }
-    if (rc == JDSP_OK) st->seen += n_blocks;
+    if (rc == JDSP_OK && advance) st->seen += n_blocks;
     return rc;
 }
 
@@ -141,11 +149,32 @@ int jdsp_fastconv_mix_i16_dev(jdsp_ctx *c, jdsp_fastconv_state *st, int sources_
                               long n_blocks, int16_t *d_out, long out_pitch, float *d_out_f32, long f32_pitch, long *n_out_blocks) {
     return fastconv_run(c, st, sources_per_scene, d_in, in_pitch, n_blocks, d_out, out_pitch, d_out_f32, f32_pitch, n_out_blocks);
 }
+int jdsp_fastconv_i16_host(jdsp_ctx *c, jdsp_fastconv_state *st, const int16_t *in, long in_pitch, long n_samples, int16_t *out, long out_pitch,
+                           long *n_out_samples) {
+    REQUIRE(c && st && in && out, "null argument");
+    REQUIRE(n_samples >= 0, "bad size");
+    const jdsp_fastconv_params &p = st->p;
+    const long B = p.block, nb = (n_samples + B - 1) / B;
+    const long skip = st->seen < p.history_blocks ? p.history_blocks - st->seen : 0;
+    const long n_out = nb > skip ? (nb - skip) * B : 0;
+    if (n_out_samples) *n_out_samples = n_out;
+    if (nb == 0) return JDSP_OK;
+    REQUIRE(in_pitch >= n_samples && (n_out == 0 || out_pitch >= n_out), "row pitch smaller than a row");
+    CU(cudaSetDevice(c->device));
+    const long row_in = nb * B, row_out = n_out > 0 ? n_out : 8;
+    TRY(pipe_rows(c, st->n_sources, in, in_pitch * sizeof(int16_t), n_samples * sizeof(int16_t), row_in * sizeof(int16_t), out, out_pitch * sizeof(int16_t),
+                  n_out * sizeof(int16_t), row_out * sizeof(int16_t), [&](long s0, long ns, void *d_in, void *d_out) {
+                      TRY(apply_stale_tail(c, (int16_t *)d_in, row_in, ns, n_samples, (int)B));
+                      return fastconv_run(c, st, 1, (const int16_t *)d_in, row_in, nb, (int16_t *)d_out, row_out, nullptr, 0, nullptr, s0, ns, false);
+                  }, p.n_ears));
+    st->seen += nb;
+    return JDSP_OK;
+}
 int jdsp_fastconv_i16(jdsp_ctx *c, const jdsp_fastconv_params *p, const double *taps, const int16_t *pcm, long n_samples, int16_t *out,
                       long out_pitch, long *n_out_samples) {
     REQUIRE(c && p && taps && pcm && out, "null argument");
     REQUIRE(n_samples >= 0, "bad size");
-    const long B = p->block, nb = (n_samples + B - 1) / B;
+    const long B = p->block, nb = B > 0 ? (n_samples + B - 1) / B : 0;
     const long n_out = nb > p->history_blocks ? (nb - p->history_blocks) * B : 0;
     if (n_out_samples) *n_out_samples = n_out;
     if (n_out == 0) return JDSP_OK;
@@ -154,24 +183,7 @@ int jdsp_fastconv_i16(jdsp_ctx *c, const jdsp_fastconv_params *p, const double *
     pp.shared_filter = 1;
     jdsp_fastconv_state *st = nullptr;
     TRY(jdsp_fastconv_state_create(c, &pp, 1, taps, &st));
-    const long pitch = nb * B;
-    int16_t *d_in = nullptr, *d_out = nullptr;
-    int rc = JDSP_OK;
-    cudaError_t e = cudaMalloc((void **)&d_in, pitch * sizeof(int16_t));
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_out, p->n_ears * pitch * sizeof(int16_t));
-    if (e == cudaSuccess) e = cudaMemsetAsync(d_in, 0, pitch * sizeof(int16_t), c->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, pcm, n_samples * sizeof(int16_t), cudaMemcpyHostToDevice, c->stream);
-    if (e != cudaSuccess) rc = fail(JDSP_ERR_CUDA, std::string("fastconv_i16 setup: ") + cudaGetErrorString(e));
-    if (rc == JDSP_OK) rc = apply_stale_tail(c, d_in, pitch, 1, n_samples, (int)B);
-    if (rc == JDSP_OK) rc = jdsp_fastconv_i16_dev(c, st, d_in, pitch, nb, d_out, pitch, nullptr, 0, nullptr);
-    if (rc == JDSP_OK) {
-        e = cudaMemcpy2DAsync(out, out_pitch * sizeof(int16_t), d_out, pitch * sizeof(int16_t), n_out * sizeof(int16_t), p->n_ears,
-                              cudaMemcpyDeviceToHost, c->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-        if (e != cudaSuccess) rc = fail(JDSP_ERR_CUDA, std::string("fastconv_i16: ") + cudaGetErrorString(e));
-    }
-    cudaFree(d_in);
-    cudaFree(d_out);
+    const int rc = jdsp_fastconv_i16_host(c, st, pcm, n_samples, n_samples, out, out_pitch, nullptr);
     jdsp_fastconv_state_destroy(c, st);
     return rc;
 }
@@ -220,7 +232,7 @@ int jdsp_mfcc_plan_create(jdsp_ctx *c, const jdsp_mfcc_params *p, jdsp_mfcc_plan
     REQUIRE(c && p && out, "null argument");
     if (p->n_fft != 512 && p->n_fft != 1024) return fail(JDSP_ERR_UNSUPPORTED, "MFCC supports n_fft 512 or 1024");
     REQUIRE(p->frame_len >= 8 && p->frame_len <= p->n_fft && p->frame_len % 8 == 0, "frame_len must be a multiple of 8 and <= n_fft");
-    REQUIRE(p->hop >= 8 && p->hop % 8 == 0, "hop must be a multiple of 8 samples (16-byte bulk copies)");
+    REQUIRE(p->hop >= 8 && p->hop % 8 == 0 && p->hop <= 4 * p->n_fft, "hop must be a multiple of 8 samples (16-byte bulk copies), at most 4 * n_fft");
     REQUIRE(p->n_mel >= 1 && p->n_mel <= 64 && p->n_cep >= 1 && p->n_cep <= 16, "n_mel <= 64 and n_cep <= 16");
     CU(cudaSetDevice(c->device));
     jdsp_mfcc_plan *pl = new jdsp_mfcc_plan();
@@ -284,12 +296,13 @@ int jdsp_mfcc_plan_create(jdsp_ctx *c, const jdsp_mfcc_params *p, jdsp_mfcc_plan
     }
     std::vector<float> wh(W);
     for (int i = 0; i < W; ++i) wh[i] = (float)(0.5 * (p->win_a0 - p->win_a1 * cos(2 * p->pi_literal * i / (W - 1))));
-    TRY(upload(c, wh, &pl->d_win_half));
-    TRY(upload(c, dct, &pl->d_dct));
-    TRY(upload(c, slot_w, &pl->d_slot_w));
-    TRY(upload(c, slot_ctl, &pl->d_slot_ctl));
-    TRY(upload(c, slot_pid, &pl->d_slot_pid));
-    TRY(upload(c, run_start, &pl->d_run_start));
+    int rc = upload(c, wh, &pl->d_win_half);
+    if (rc == JDSP_OK) rc = upload(c, dct, &pl->d_dct);
+    if (rc == JDSP_OK) rc = upload(c, slot_w, &pl->d_slot_w);
+    if (rc == JDSP_OK) rc = upload(c, slot_ctl, &pl->d_slot_ctl);
+    if (rc == JDSP_OK) rc = upload(c, slot_pid, &pl->d_slot_pid);
+    if (rc == JDSP_OK) rc = upload(c, run_start, &pl->d_run_start);
+    if (rc != JDSP_OK) { jdsp_mfcc_plan_destroy(c, pl); return rc; }
     *out = pl;
     return JDSP_OK;
 }
@@ -340,6 +353,24 @@ int jdsp_mfcc_frames_i16_dev(jdsp_ctx *c, jdsp_mfcc_plan *pl, const int16_t *d_i
     // samples (the bench preset's 400 of 512)
     if (NC == 256) return p.frame_len <= 13 * 32 ? launch_mfcc<256, 13>(c, a) : launch_mfcc<256, 16>(c, a);
     return launch_mfcc<512, 16>(c, a);
+}
+
+int jdsp_mfcc_frames_i16(jdsp_ctx *c, jdsp_mfcc_plan *pl, const int16_t *in, long in_pitch, long n_utts, long n_samples, float *feat,
+                         long feat_pitch, long *n_frames) {
+    REQUIRE(c && pl && in, "null argument");
+    REQUIRE(n_utts >= 0 && n_samples >= 0, "bad size");
+    const jdsp_mfcc_params &p = pl->p;
+    const long nf = n_samples >= p.frame_len ? (n_samples - p.frame_len) / p.hop + 1 : 0;
+    if (n_frames) *n_frames = nf;
+    if (nf == 0 || n_utts == 0) return JDSP_OK;
+    REQUIRE(feat, "feat is null");
+    REQUIRE(in_pitch >= n_samples && feat_pitch >= nf * p.n_cep, "row pitch smaller than a row");
+    CU(cudaSetDevice(c->device));
+    const long row_in = (n_samples + 7) & ~7L, row_out = nf * p.n_cep;
+    return pipe_rows(c, n_utts, in, in_pitch * sizeof(int16_t), n_samples * sizeof(int16_t), row_in * sizeof(int16_t), feat, feat_pitch * sizeof(float),
+                     row_out * sizeof(float), row_out * sizeof(float), [&](long, long nu, void *d_in, void *d_out) {
+                         return jdsp_mfcc_frames_i16_dev(c, pl, (const int16_t *)d_in, row_in, nu, n_samples, (float *)d_out, row_out, nullptr);
+                     });
 }
 
 int jdsp_mfcc_program_i16(jdsp_ctx *c, const jdsp_mfcc_params *p, const int16_t *pcm, long n_samples, double *rows, long *n_rows) {

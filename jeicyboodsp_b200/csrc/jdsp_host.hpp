@@ -49,6 +49,7 @@ struct jdsp_ctx {
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
     cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t pipe_ev[3] = {nullptr, nullptr, nullptr};   // "kernel of the chunk on pipe[i] is enqueued": orders kernels that share a state object
     // workspace of the host-buffer forms, kept across calls (cudaMalloc/cudaFree per call cost more than the copies)
     void *ws_in[3] = {nullptr, nullptr, nullptr}, *ws_out[3] = {nullptr, nullptr, nullptr};
     size_t ws_in_bytes = 0, ws_out_bytes = 0;
@@ -173,16 +174,23 @@ static int ensure_workspace(jdsp_ctx *c, size_t in_bytes, size_t out_bytes, int 
 //   d_in_row / d_out_row   bytes per row of the device staging buffers (>= the copied bytes; the launcher may pad rows)
 //   launch(u0, nu, d_in, d_out)  enqueues the kernels for rows [u0, u0 + nu) on c->stream (which is the chunk's pipe stream
 //                                for the duration of the call)
+//   out_mult        output rows per input row (fast-conv: one per ear); out_pitch / out_copy / d_out_row describe ONE output row
+// bytes per chunk of the host-buffer forms (JDSP_HOST_CHUNK_BYTES overrides: tests use it to force many small chunks)
+static size_t host_chunk_bytes() {
+    if (const char *e = getenv("JDSP_HOST_CHUNK_BYTES")) { const long v = atol(e); if (v > 0) return (size_t)v; }
+    return (size_t)128 << 20;
+}
 template <class Launch>
 static int pipe_rows(jdsp_ctx *c, long n_rows, const void *in, size_t in_pitch, size_t in_copy, size_t d_in_row, void *out, size_t out_pitch,
-                     size_t out_copy, size_t d_out_row, Launch launch, size_t chunk_bytes = (size_t)128 << 20) {
+                     size_t out_copy, size_t d_out_row, Launch launch, int out_mult = 1) {
     if (n_rows <= 0) return JDSP_OK;
-    const size_t row = d_in_row > d_out_row ? d_in_row : d_out_row;
+    const size_t chunk_bytes = host_chunk_bytes();
+    const size_t row = d_in_row > d_out_row * out_mult ? d_in_row : d_out_row * out_mult;
     long chunk = (long)(chunk_bytes / (row ? row : 1));
     if (chunk < 1) chunk = 1;
     if (chunk > n_rows) chunk = n_rows;
     const int nslots = (n_rows + chunk - 1) / chunk > 1 ? 3 : 1;
-    TRY(ensure_workspace(c, (size_t)chunk * d_in_row, (size_t)chunk * d_out_row, nslots));
+    TRY(ensure_workspace(c, (size_t)chunk * d_in_row, (size_t)chunk * d_out_row * out_mult, nslots));
     CU(cudaStreamSynchronize(c->stream));   // whatever the caller enqueued (state resets, table uploads) is done before the pipe streams start
     int rc = JDSP_OK, slot = 0;
     cudaStream_t saved = c->stream;
@@ -200,10 +208,10 @@ static int pipe_rows(jdsp_ctx *c, long n_rows, const void *in, size_t in_pitch, 
         rc = launch(u0, nu, c->ws_in[slot], c->ws_out[slot]);
         c->stream = saved;
         if (rc != JDSP_OK) break;
-        char *dst = (char *)out + (size_t)u0 * out_pitch;
+        char *dst = (char *)out + (size_t)u0 * out_mult * out_pitch;
         if (out_copy > 0) {
-            if (out_pitch == out_copy && d_out_row == out_copy) e = cudaMemcpyAsync(dst, c->ws_out[slot], (size_t)nu * out_copy, cudaMemcpyDeviceToHost, q);
-            else e = cudaMemcpy2DAsync(dst, out_pitch, c->ws_out[slot], d_out_row, out_copy, (size_t)nu, cudaMemcpyDeviceToHost, q);
+            if (out_pitch == out_copy && d_out_row == out_copy) e = cudaMemcpyAsync(dst, c->ws_out[slot], (size_t)nu * out_mult * out_copy, cudaMemcpyDeviceToHost, q);
+            else e = cudaMemcpy2DAsync(dst, out_pitch, c->ws_out[slot], d_out_row, out_copy, (size_t)nu * out_mult, cudaMemcpyDeviceToHost, q);
         }
         if (e != cudaSuccess) { rc = fail(JDSP_ERR_CUDA, std::string("host form D2H: ") + cudaGetErrorString(e)); break; }
     }

@@ -41,8 +41,9 @@ int jdsp_pitch_state_create(jdsp_ctx *c, const jdsp_pitch_params *p, long n_stre
     jdsp_pitch_state *st = new jdsp_pitch_state();
     st->p = *p;
     st->n_streams = n_streams;
-    CU(cudaMalloc((void **)&st->d_prev, n_streams * p->block * sizeof(int16_t)));
-    TRY(jdsp_pitch_state_reset(c, st));
+    int rc = cudaMalloc((void **)&st->d_prev, n_streams * p->block * sizeof(int16_t)) == cudaSuccess ? JDSP_OK : fail(JDSP_ERR_CUDA, "pitch state allocation failed");
+    if (rc == JDSP_OK) rc = jdsp_pitch_state_reset(c, st);
+    if (rc != JDSP_OK) { jdsp_pitch_state_destroy(c, st); return rc; }
     *out = st;
     return JDSP_OK;
 }

@@ -21,6 +21,7 @@ int jdsp_roundtrip_i16_dev(jdsp_ctx *c, const int16_t *d_in, long in_pitch, int1
     REQUIRE(c && d_in && d_out, "null argument");
     REQUIRE(n_streams >= 0 && n_blocks >= 0, "negative size");
     REQUIRE(in_pitch % 2 == 0 && out_pitch % 2 == 0, "pitches must be even (4-byte aligned rows)");
+    if (!is_pow2(n_fft) || n_fft < 64 || n_fft > 4096) return fail(JDSP_ERR_UNSUPPORTED, "round trip supports n_fft = 64..4096 (power of two)");
     if (n_streams == 0 || n_blocks == 0) return JDSP_OK;
     CU(cudaSetDevice(c->device));
     void *tw;
@@ -37,30 +38,27 @@ int jdsp_roundtrip_i16_dev(jdsp_ctx *c, const int16_t *d_in, long in_pitch, int1
         default: return fail(JDSP_ERR_UNSUPPORTED, "round trip supports n_fft = 64..4096 (power of two)");
     }
 }
+int jdsp_roundtrip_batch_i16(jdsp_ctx *c, const int16_t *in, long in_pitch, long n_streams, long n_samples, int n_fft, int16_t *out,
+                             long out_pitch, long *n_out) {
+    REQUIRE(c && in && out, "null argument");
+    REQUIRE(n_streams >= 1 && n_samples >= 0 && n_fft > 0, "bad size");
+    if (!is_pow2(n_fft) || n_fft < 64 || n_fft > 4096) return fail(JDSP_ERR_UNSUPPORTED, "round trip supports n_fft = 64..4096 (power of two)");
+    const long nb = (n_samples + n_fft - 1) / n_fft, row = nb * n_fft;
+    if (n_out) *n_out = row;
+    if (nb == 0) return JDSP_OK;
+    REQUIRE(in_pitch >= n_samples && out_pitch >= row, "row pitch smaller than a row");
+    CU(cudaSetDevice(c->device));
+    return pipe_rows(c, n_streams, in, in_pitch * sizeof(int16_t), n_samples * sizeof(int16_t), row * sizeof(int16_t), out, out_pitch * sizeof(int16_t),
+                     row * sizeof(int16_t), row * sizeof(int16_t), [&](long, long ns, void *d_in, void *d_out) {
+                         TRY(apply_stale_tail(c, (int16_t *)d_in, row, ns, n_samples, n_fft));
+                         return jdsp_roundtrip_i16_dev(c, (const int16_t *)d_in, row, (int16_t *)d_out, row, nullptr, 0, n_fft, ns, nb);
+                     });
+}
 int jdsp_roundtrip_i16(jdsp_ctx *c, const int16_t *pcm, long n_samples, int n_fft, int16_t *out, long *n_out) {
     REQUIRE(c && pcm && out, "null argument");
     REQUIRE(n_samples >= 0 && n_fft > 0, "bad size");
-    const long nb = (n_samples + n_fft - 1) / n_fft;
-    if (n_out) *n_out = nb * n_fft;
-    if (nb == 0) return JDSP_OK;
-    CU(cudaSetDevice(c->device));
-    const long pitch = nb * n_fft;
-    int16_t *d_in = nullptr, *d_out = nullptr;
-    CU(cudaMalloc((void **)&d_in, pitch * sizeof(int16_t)));
-    CU(cudaMalloc((void **)&d_out, pitch * sizeof(int16_t)));
-    int rc = JDSP_OK;
-    do {
-        if (cudaMemsetAsync(d_in, 0, pitch * sizeof(int16_t), c->stream) != cudaSuccess ||
-            cudaMemcpyAsync(d_in, pcm, n_samples * sizeof(int16_t), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { rc = fail(JDSP_ERR_CUDA, "H2D copy failed"); break; }
-        if ((rc = apply_stale_tail(c, d_in, pitch, 1, n_samples, n_fft)) != JDSP_OK) break;
-        if ((rc = jdsp_roundtrip_i16_dev(c, d_in, pitch, d_out, pitch, nullptr, 0, n_fft, 1, nb)) != JDSP_OK) break;
-        if (cudaMemcpyAsync(out, d_out, pitch * sizeof(int16_t), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { rc = fail(JDSP_ERR_CUDA, "D2H copy failed"); break; }
-        cudaError_t e = cudaStreamSynchronize(c->stream);
-        if (e != cudaSuccess) rc = fail(JDSP_ERR_CUDA, std::string("roundtrip: ") + cudaGetErrorString(e));
-    } while (0);
-    cudaFree(d_in);
-    cudaFree(d_out);
-    return rc;
+    const long row = (n_samples + n_fft - 1) / n_fft * n_fft;
+    return jdsp_roundtrip_batch_i16(c, pcm, n_samples, 1, n_samples, n_fft, out, row, n_out);
 }
 }  // extern "C"
 
@@ -130,13 +128,17 @@ int jdsp_denoise_state_create(jdsp_ctx *c, const jdsp_denoise_params *p, long n_
     st->p = *p;
     st->n_streams = n_streams;
     const long S = n_streams, NC = p->n_fft / 2, H = p->hop, N = p->n_fft;
-    CU(cudaMalloc((void **)&st->d_seen, S * sizeof(int32_t)));
-    CU(cudaMalloc((void **)&st->d_run, S * sizeof(int32_t)));
-    CU(cudaMalloc((void **)&st->d_pub, S * sizeof(int32_t)));
-    CU(cudaMalloc((void **)&st->d_avg, S * (NC + 1) * sizeof(float)));
-    CU(cudaMalloc((void **)&st->d_ns, S * (NC + 1) * sizeof(float)));
-    CU(cudaMalloc((void **)&st->d_ola, S * H * sizeof(float)));
-    CU(cudaMalloc((void **)&st->d_prev, S * H * sizeof(int16_t)));
+    const int rc_alloc = [&]() -> int {
+        CU(cudaMalloc((void **)&st->d_seen, S * sizeof(int32_t)));
+        CU(cudaMalloc((void **)&st->d_run, S * sizeof(int32_t)));
+        CU(cudaMalloc((void **)&st->d_pub, S * sizeof(int32_t)));
+        CU(cudaMalloc((void **)&st->d_avg, S * (NC + 1) * sizeof(float)));
+        CU(cudaMalloc((void **)&st->d_ns, S * (NC + 1) * sizeof(float)));
+        CU(cudaMalloc((void **)&st->d_ola, S * H * sizeof(float)));
+        CU(cudaMalloc((void **)&st->d_prev, S * H * sizeof(int16_t)));
+        return JDSP_OK;
+    }();
+    if (rc_alloc != JDSP_OK) { jdsp_denoise_state_destroy(c, st); return rc_alloc; }
     // window in double with the program's PI literal (:226); the kernel takes 0.5*w in float for the transform
     // and w[H..N) in double for the bit-exact VAD (:131)
     std::vector<float> wh((size_t)N);
@@ -146,9 +148,10 @@ int jdsp_denoise_state_create(jdsp_ctx *c, const jdsp_denoise_params *p, long n_
         wh[i] = (float)(0.5 * w);
         if (i >= H) wv[i - H] = w;
     }
-    TRY(upload(c, wh, &st->d_win_half));
-    TRY(upload(c, wv, &st->d_win_vad));
-    TRY(jdsp_denoise_state_reset(c, st));
+    int rc = upload(c, wh, &st->d_win_half);
+    if (rc == JDSP_OK) rc = upload(c, wv, &st->d_win_vad);
+    if (rc == JDSP_OK) rc = jdsp_denoise_state_reset(c, st);
+    if (rc != JDSP_OK) { jdsp_denoise_state_destroy(c, st); return rc; }
     *out = st;
     return JDSP_OK;
 }
@@ -297,50 +300,55 @@ int jdsp_denoise_i16(jdsp_ctx *c, const jdsp_denoise_params *p, const int16_t *i
     } else {
         TRY(jdsp_denoise_state_reset(c, st));
     }
-    // chunks of streams ride three CUDA streams so H2D, compute and D2H of neighbouring chunks overlap
-    const long row_in = nb * H, row_out = n_out > 0 ? n_out : 8;
-    long chunk = (128L << 20) / (long)(row_in * sizeof(int16_t));
-    if (chunk < 1) chunk = 1;
-    if (chunk > n_streams) chunk = n_streams;
-    const int nslots = (n_streams + chunk - 1) / chunk > 1 ? 3 : 1;
-    TRY(ensure_workspace(c, (size_t)chunk * row_in * sizeof(int16_t), (size_t)chunk * row_out * sizeof(int16_t), nslots));
-    int16_t *d_in[3], *d_out[3];
-    for (int i = 0; i < 3; ++i) { d_in[i] = (int16_t *)c->ws_in[i]; d_out[i] = (int16_t *)c->ws_out[i]; }
+    // Chunks along TIME ride three CUDA streams so that the host-to-device copy of chunk i+1, the kernel of chunk i and the
+    // device-to-host copy of chunk i-1 overlap: every chunk holds T consecutive blocks of ALL streams, so each launch is a full
+    // device of streams for the stream-group kernel (chunks of streams, the round-1 form, left 69-stream launches to the
+    // CTA-per-stream kernel); the per-stream state object carries a stream from chunk to chunk, events keep the kernels in order.
+    long T = (long)(host_chunk_bytes() / (size_t)(n_streams * H * sizeof(int16_t)));
+    if (T < 4) T = 4;
+    if (T > nb) T = nb;
+    const long TP = T + 1;             // row pitch of a chunk in blocks: the last chunk absorbs a one-block remainder, so that the
+                                       // block before a short final block (source of its stale tail) sits in the same chunk
+    const int nslots = nb > TP ? 3 : 1;
+    TRY(ensure_workspace(c, (size_t)n_streams * TP * H * sizeof(int16_t), (size_t)n_streams * TP * H * sizeof(int16_t), nslots));
+    for (int i = 0; i < 3; ++i)
+        if (!c->pipe_ev[i]) CU(cudaEventCreateWithFlags(&c->pipe_ev[i], cudaEventDisableTiming));
     int rc = JDSP_OK;
     cudaError_t e = cudaSuccess;
-    {
-        cudaStreamSynchronize(c->stream);  // state reset done before the pipe streams touch it
-        int slot = 0;
-        for (long s0 = 0; s0 < n_streams && rc == JDSP_OK; s0 += chunk, slot = (slot + 1) % nslots) {
-            const long ns = n_streams - s0 < chunk ? n_streams - s0 : chunk;
-            cudaStream_t q = c->pipe[slot];
-            if (in_pitch == row_in && n_samples == row_in)   // contiguous rows: one linear copy (full PCIe rate, overlaps with D2H)
-                e = cudaMemcpyAsync(d_in[slot], in + s0 * in_pitch, (size_t)ns * row_in * sizeof(int16_t), cudaMemcpyHostToDevice, q);
-            else
-                e = cudaMemcpy2DAsync(d_in[slot], row_in * sizeof(int16_t), in + s0 * in_pitch, in_pitch * sizeof(int16_t),
-                                      n_samples * sizeof(int16_t), ns, cudaMemcpyHostToDevice, q);
-            if (e != cudaSuccess) { rc = fail(JDSP_ERR_CUDA, std::string("denoise_i16 H2D: ") + cudaGetErrorString(e)); break; }
-            if (n_samples % H) {
-                cudaStream_t saved = c->stream; c->stream = q;
-                rc = apply_stale_tail(c, d_in[slot], row_in, ns, n_samples, (int)H);
-                c->stream = saved;
-                if (rc != JDSP_OK) break;
-            }
-            rc = denoise_launch_slice(c, st, q, s0, ns, d_in[slot], row_in, nb, d_out[slot], row_out, nullptr, 0, nullptr);
+    cudaStreamSynchronize(c->stream);  // state reset done before the pipe streams touch it
+    long emitted = 0;
+    int slot = 0, prev_slot = -1;
+    for (long b0 = 0, tb = 0; b0 < nb && rc == JDSP_OK; b0 += tb, prev_slot = slot, slot = (slot + 1) % nslots) {
+        tb = nb - b0 <= TP ? nb - b0 : T;
+        const long have = n_samples - b0 * H < tb * H ? n_samples - b0 * H : tb * H;   // samples of this chunk present in the input
+        cudaStream_t q = c->pipe[slot];
+        int16_t *d_in = (int16_t *)c->ws_in[slot], *d_out = (int16_t *)c->ws_out[slot];
+        e = cudaMemcpy2DAsync(d_in, TP * H * sizeof(int16_t), in + b0 * H, in_pitch * sizeof(int16_t), have * sizeof(int16_t), n_streams, cudaMemcpyHostToDevice, q);
+        if (e != cudaSuccess) { rc = fail(JDSP_ERR_CUDA, std::string("denoise_i16 H2D: ") + cudaGetErrorString(e)); break; }
+        if (have < tb * H) {   // short final block: it keeps the previous block's samples there (:94)
+            cudaStream_t saved = c->stream; c->stream = q;
+            rc = apply_stale_tail(c, d_in, TP * H, n_streams, have, (int)H);
+            c->stream = saved;
             if (rc != JDSP_OK) break;
-            if (n_out > 0) {
-                if (out_pitch == row_out)
-                    e = cudaMemcpyAsync(out + s0 * out_pitch, d_out[slot], (size_t)ns * row_out * sizeof(int16_t), cudaMemcpyDeviceToHost, q);
-                else
-                    e = cudaMemcpy2DAsync(out + s0 * out_pitch, out_pitch * sizeof(int16_t), d_out[slot], row_out * sizeof(int16_t),
-                                          n_out * sizeof(int16_t), ns, cudaMemcpyDeviceToHost, q);
-                if (e != cudaSuccess) { rc = fail(JDSP_ERR_CUDA, std::string("denoise_i16 D2H: ") + cudaGetErrorString(e)); break; }
-            }
         }
-        for (int i = 0; i < nslots; ++i) {
-            e = cudaStreamSynchronize(c->pipe[i]);
-            if (e != cudaSuccess && rc == JDSP_OK) rc = fail(JDSP_ERR_CUDA, std::string("denoise_i16: ") + cudaGetErrorString(e));
+        if (prev_slot >= 0 && prev_slot != slot) {
+            e = cudaStreamWaitEvent(q, c->pipe_ev[prev_slot], 0);
+            if (e != cudaSuccess) { rc = fail(JDSP_ERR_CUDA, std::string("denoise_i16 order: ") + cudaGetErrorString(e)); break; }
         }
+        const long skip = st->seen < 2 ? 2 - st->seen : 0;
+        const long em = tb > skip ? tb - skip : 0;
+        rc = denoise_launch_slice(c, st, q, 0, n_streams, d_in, TP * H, tb, d_out, TP * H, nullptr, 0, nullptr);
+        if (rc != JDSP_OK) break;
+        st->seen += tb;
+        e = cudaEventRecord(c->pipe_ev[slot], q);
+        if (e == cudaSuccess && em > 0)
+            e = cudaMemcpy2DAsync(out + emitted * H, out_pitch * sizeof(int16_t), d_out, TP * H * sizeof(int16_t), em * H * sizeof(int16_t), n_streams, cudaMemcpyDeviceToHost, q);
+        if (e != cudaSuccess) { rc = fail(JDSP_ERR_CUDA, std::string("denoise_i16 D2H: ") + cudaGetErrorString(e)); break; }
+        emitted += em;
+    }
+    for (int i = 0; i < 3; ++i) {
+        e = cudaStreamSynchronize(c->pipe[i]);
+        if (e != cudaSuccess && rc == JDSP_OK) rc = fail(JDSP_ERR_CUDA, std::string("denoise_i16: ") + cudaGetErrorString(e));
     }
     return rc;
 }

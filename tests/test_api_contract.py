@@ -26,6 +26,10 @@ def test_invalid_arguments_are_rejected(be):
     with pytest.raises(JdspError) as e:
         be.ctx.fft_c2c_f32(be.zeros((1, 1 << 17), np.complex64), be.zeros((1, 1 << 17), np.complex64), 1 << 17, 1, True)
     assert e.value.code == -4                                  # JDSP_ERR_UNSUPPORTED above 2^16
+    for bad_n in (1000, 100, 8192):                            # round trip: lengths outside 64..4096 or not powers of two are refused
+        with pytest.raises(JdspError) as e:                    # up front (1000 once spun forever building a twiddle table)
+            be.ctx.roundtrip(np.zeros(3000, np.int16), bad_n)
+        assert e.value.code == -4
     p = be.L.denoise_params("bench", SS)
     p.n_fft = 2048                                             # n_fft != 2*hop
     with pytest.raises(JdspError):

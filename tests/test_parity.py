@@ -211,11 +211,13 @@ def test_denoise_dev_state_machine_and_precast(be, dkernel, oracle, preset, mode
     st.close()
 
 
+@pytest.mark.parametrize("mode", [SS, WIENER])
 @pytest.mark.parametrize("preset", ["bench", "ref"])
-def test_denoise_chunked_equals_one_shot(be, dkernel, preset):
+def test_denoise_chunked_equals_one_shot(be, dkernel, preset, mode):
     """The explicit stream state replaces the reference's statics: feeding a stream in pieces of whole blocks
-    (including pieces shorter than the 2-block warm-up) must give bit-identical output."""
-    p = be.L.denoise_params(preset, SS)
+    (including pieces shorter than the 2-block warm-up) must give bit-identical output -- in Wiener mode too, whose
+    published noise spectrum is stored as ns and carried in the kernels as ns^2/N."""
+    p = be.L.denoise_params(preset, mode)
     H, nb, S = p.hop, 61, 2
     x = np.stack([synth.denoise_stream(40 + s, nb * H) for s in range(S)])
     one = be.ctx.denoise(x, p)
@@ -420,6 +422,60 @@ def test_mfcc_bench_framing(be, oracle):
     for u in range(U):
         assert_float_parity(feat[u], oracle.mfcc_frames(x[u], OMP.preset("bench")), "mfcc bench")
     plan.close()
+
+
+# ---- host-buffer forms: chunked copy / compute pipelines must return exactly what one device-resident call returns ----------
+def test_host_forms_chunked_equal_resident(be, oracle, monkeypatch):
+    import ctypes as C
+    from jeicyboodsp_b200.binding import _ptr
+    monkeypatch.setenv("JDSP_HOST_CHUNK_BYTES", "20000")       # a few rows / a few blocks per chunk: many chunks, all three slots
+    ctx, L = be.ctx, be.L
+    # denoise: chunks along time, ragged final block (stale tail), both modes
+    for mode in (SS, WIENER):
+        p = L.denoise_params("bench", mode)
+        n = 41 * p.hop + 77
+        x = np.stack([synth.denoise_stream(s, n) for s in range(5)])
+        got = ctx.denoise(x, p)
+        for s in (0, 4):
+            assert_i16_parity(got[s], oracle.denoise(x[s], ODP.preset("bench", mode)).out, 2e-3, "denoise host")
+        monkeypatch.setenv("JDSP_HOST_CHUNK_BYTES", str(1 << 30))
+        assert np.array_equal(ctx.denoise(x, p), got)          # one chunk == many chunks, bit for bit
+        monkeypatch.setenv("JDSP_HOST_CHUNK_BYTES", "20000")
+    # round trip on many streams
+    sig = np.stack([np.roll(synth.roundtrip_signal(5000), 31 * s) for s in range(7)])
+    out = np.zeros((7, 5120), np.int16)
+    assert ctx.roundtrip_batch_raw(sig, 5000, 7, 5000, 512, out, 5120) == 5120
+    for s in range(7):
+        assert np.array_equal(out[s], ctx.roundtrip(sig[s], 512))
+    # fast convolution: state-based host form over chunks of sources, two ears, ragged final block
+    pf = L.fastconv_params("bench")
+    S, n = 6, 9 * pf.block + 100
+    rng = np.random.default_rng(11)
+    xs = rng.integers(-3000, 3000, (S, n)).astype(np.int16)
+    taps = np.zeros((S, 2, pf.n_taps)); taps[:, :, 8] = 1.0; taps[:, :, 9:60] = rng.normal(0, 0.05, (S, 2, 51))
+    st = ctx.fastconv_state(pf, S, taps)
+    n_out = 9 * pf.block
+    ho = np.zeros((S, 2, n_out), np.int16)
+    assert st.run_host(xs, n, n, ho, n_out) == n_out
+    st.close()
+    for s in (0, 3, 5):
+        assert np.array_equal(ho[s], ctx.fastconv(xs[s], taps[s], pf))
+    # MFCC over chunks of utterances
+    pm = L.mfcc_params("bench")
+    U, nu = 9, pm.frame_len + 11 * pm.hop
+    xu = np.stack([synth.mfcc_utterance(u, nu) for u in range(U)])
+    plan = ctx.mfcc_plan(pm)
+    hf = np.zeros((U, 12, pm.n_cep), np.float32)
+    assert plan.run_host(xu, nu, U, nu, hf, 12 * pm.n_cep) == 12
+    d_feat = be.zeros((U, 12, pm.n_cep), np.float32)
+    plan.run(be.to_dev(xu), nu, U, nu, d_feat, 12 * pm.n_cep)
+    assert np.array_equal(hf, be.to_host(d_feat))
+    plan.close()
+    # batched fp32 transform on host buffers
+    z = (rng.uniform(-1, 1, (40, 256)) + 1j * rng.uniform(-1, 1, (40, 256))).astype(np.complex64)
+    zo = np.zeros_like(z)
+    ctx.fft_c2c_f32_host(z, zo, 256, 40, True)
+    assert np.abs(zo - np.fft.fft(z.astype(np.complex128))).max() < 1e-4 * np.abs(np.fft.fft(z)).max()
 
 
 # ---- pitch (PitchEstimation_method1) ---------------------------------------------------------
