@@ -672,23 +672,22 @@ def main_gpu(args):
     if rank == 0 and not args.no_parity:
         from oracle.oracle import DenoiseParams as ODP
         pick = sorted(set([0, 1, S // 2 - 1, S - 1] + [int(v) for v in np.random.default_rng(2).integers(0, S, 4)]))
-        worst, flips, total, pubs, skipped = 0, 0, 0, [], 0
+        worst, flips, total, pubs, ambiguous = 0, 0, 0, [], 0
         for m in (SS, WIENER):
             states[m].reset()
             states[m].run(x, n, nb, out, n_out)
             got = out[pick].cpu().numpy()
             for i, s in enumerate(pick):
                 r = B.oracle.denoise(x[s].cpu().numpy(), ODP.preset("bench", m))
-                # a block at zcr == thr-1 with low energy is undecidable: the reference reads one element past its buffer there
-                # (SURVEY appendix C-3); the tests skip such streams and so does this check
-                if bool(np.any((r.zcr == params[m].zcr_thr - 1) & (r.energy <= params[m].energy_thr))):
-                    skipped += 1
-                    continue
+                # Blocks at zcr == thr-1 with low energy are undecidable in the REFERENCE BINARY (it reads one element past its VAD
+                # buffer); the oracle and the kernels both define that element as 0, so they are compared on
+                # every block.  The count is reported because parity against the compiled program (tests/) has to skip such streams.
+                ambiguous += int(np.sum((r.zcr == params[m].zcr_thr - 1) & (r.energy <= params[m].energy_thr)))
                 d = np.abs(got[i].astype(np.int64) - r.out.astype(np.int64))
                 worst, flips, total = max(worst, int(d.max())), flips + int((d > 0).sum()), total + d.size
                 pubs.append(len(r.publish))
-        parity = {"streams_checked": len(pick), "ambiguous_streams_skipped": skipped, "max_abs_lsb": worst, "flip_fraction": flips / max(total, 1),
-                  "oracle_publishes_min": min(pubs) if pubs else None}
+        parity = {"streams_checked": len(pick), "max_abs_lsb": worst, "flip_fraction": flips / max(total, 1), "oracle_publishes_min": min(pubs),
+                  "blocks_ambiguous_in_the_reference_binary": ambiguous}
 
     # ---- end to end through the host-buffer C-ABI call, and the raw copies alone as a control ----------------------
     e2e = None

@@ -14,7 +14,7 @@ LIB = os.path.join(HERE, "libjdsp.so")
 SOURCES = ["jdsp_api.cu", "jdsp_stft.cu", "jdsp_conv_mfcc.cu", "jdsp_pitch.cu", "jdsp_mvdr.cu"]
 COMMON = ["jdsp_host.hpp", "jdsp_device.cuh", "../../include/jdsp.h"]
 DEPS = {"jdsp_api.cu": ["kernels_fft.cuh"], "jdsp_stft.cu": ["kernels_stft.cuh", "kernels_stream.cuh"],
-        "jdsp_conv_mfcc.cu": ["kernels_conv_mfcc.cuh", "kernels_stft.cuh"],
+        "jdsp_conv_mfcc.cu": ["kernels_conv_mfcc.cuh", "kernels_fastconv.cuh", "kernels_mfcc.cuh", "kernels_stream.cuh", "kernels_stft.cuh"],
         "jdsp_pitch.cu": ["kernels_pitch.cuh", "kernels_stft.cuh"],
         "jdsp_mvdr.cu": ["kernels_mvdr.cuh", "kernels_stft.cuh"]}
 HEADERS = COMMON + sorted({h for v in DEPS.values() for h in v})

@@ -1,6 +1,7 @@
 // jdsp_conv_mfcc.cu -- C ABI (include/jdsp.h), part 3: the fast-convolution and MFCC pipelines.
 #include "jdsp_host.hpp"
 #include "kernels_conv_mfcc.cuh"
+#include "kernels_fastconv.cuh"
 #include "kernels_mfcc.cuh"
 
 // ---------------------------------------------------------------------------------------------------
@@ -97,6 +98,19 @@ template <int NC, int Q> static int launch_fastconv(jdsp_ctx *c, const FastconvA
 }
 // src0 / nsrc: the slice of the state's sources this launch covers (the host form walks the sources in chunks and advances the
 // block counter itself once every chunk has been through: `advance` false)
+// One thread group per source and time slice (kernels_fastconv.cuh): one-block history, one source per output pair.
+template <int NC> static int launch_fastconv_stream(jdsp_ctx *c, const FastconvArgs &a) {
+    using Geo = FastconvStreamGeom<NC>;
+    auto kfn = fastconv_stream_kernel<NC>;
+    TRY(opt_in_smem(kfn, Geo::SMEM));
+    int per_sm = 4;
+#ifndef JDSP_EMUL
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, Geo::NT, Geo::SMEM));
+    if (per_sm < 1) return fail(JDSP_ERR_CUDA, "fast-conv kernel does not fit an SM");
+#endif
+    JDSP_LAUNCH_PTR(kfn, dim3(grid_for(c, a.n_scenes, per_sm)), dim3(Geo::NT), Geo::SMEM, c->stream, a);
+    return launch_check(c);
+}
 static int fastconv_run(jdsp_ctx *c, jdsp_fastconv_state *st, int sources_per_scene, const int16_t *d_in, long in_pitch, long n_blocks,
                         int16_t *d_out, long out_pitch, float *d_out_f32, long f32_pitch, long *n_out_blocks, long src0 = 0, long nsrc = -1,
                         bool advance = true) {
@@ -125,6 +139,14 @@ static int fastconv_run(jdsp_ctx *c, jdsp_fastconv_state *st, int sources_per_sc
     a.B = p.block; a.q = p.history_blocks; a.n_ears = p.n_ears; a.shared_filter = p.shared_filter; a.seen0 = st->seen;
     int rc;
     const int key = NC * 16 + p.history_blocks;
+    // JDSP_FASTCONV_KERNEL=tile forces the general kernel where the stream-group kernel applies (tests compare the two)
+    const char *force = getenv("JDSP_FASTCONV_KERNEL");
+    const bool stream_ok = sources_per_scene == 1 && p.history_blocks == 1 && (NC == 256 || NC == 512) && !(force && !strcmp(force, "tile"));
+    if (stream_ok) {
+        rc = NC == 256 ? launch_fastconv_stream<256>(c, a) : launch_fastconv_stream<512>(c, a);
+        if (rc == JDSP_OK && advance) st->seen += n_blocks;
+        return rc;
+    }
     switch (key) {
         case 256 * 16 + 1: rc = launch_fastconv<256, 1>(c, a); break;
         case 512 * 16 + 1: rc = launch_fastconv<512, 1>(c, a); break;    // bench preset

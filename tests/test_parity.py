@@ -354,6 +354,44 @@ def test_fastconv_dev_many_sources_chunked_and_precast(be, oracle):
     st.close()
 
 
+@pytest.mark.parametrize("n_fft", [512, 1024])
+def test_fastconv_kernels_agree(be, oracle, monkeypatch, n_fft):
+    """The stream-group kernel (one-block history, kernels_fastconv.cuh) against the general kernel and the oracle: block
+    counts that do not divide into the CTA's time slices, calls of one and two blocks, state handed from one kernel to the other."""
+    pf = be.L.fastconv_params("bench")
+    pf.n_fft, pf.block, pf.n_taps = n_fft, n_fft // 2, n_fft // 2 + 1
+    Bk, S = pf.block, 5
+    rng = np.random.default_rng(n_fft)
+    nb = 23 if be.name == "gpu" else 9
+    xs = rng.integers(-5000, 5000, (S, nb * Bk)).astype(np.int16)
+    taps = np.zeros((S, 2, pf.n_taps)); taps[:, :, 3] = 1.0; taps[:, :, 4:Bk] = rng.normal(0, 0.04, (S, 2, Bk - 4))
+    outs = {}
+    for kern, pieces in (("stream", [nb]), ("tile", [nb]), ("stream", [1, 2, nb - 3]), ("mixed", [4, nb - 4])):
+        st = be.ctx.fastconv_state(pf, S, taps)
+        parts, pos = [], 0
+        for i, k in enumerate(pieces):
+            if kern == "tile" or (kern == "mixed" and i == 0):
+                monkeypatch.setenv("JDSP_FASTCONV_KERNEL", "tile")
+            else:
+                monkeypatch.delenv("JDSP_FASTCONV_KERNEL", raising=False)
+            d_out = be.zeros((S, 2, k * Bk), np.int16)
+            em = st.run(be.to_dev(xs[:, pos * Bk:(pos + k) * Bk]), k * Bk, k, d_out, k * Bk)
+            parts.append(be.to_host(d_out)[:, :, : em * Bk].copy())
+            pos += k
+        st.close()
+        outs[(kern, len(pieces))] = np.concatenate(parts, axis=2)
+    monkeypatch.delenv("JDSP_FASTCONV_KERNEL", raising=False)
+    one = outs[("stream", 1)]
+    assert one.shape == (S, 2, (nb - 1) * Bk)
+    assert np.array_equal(outs[("stream", 3)], one)                      # chunked == one shot, bit for bit
+    for key in (("tile", 1), ("mixed", 2)):
+        assert np.abs(outs[key].astype(int) - one.astype(int)).max() <= 1   # two summation orders: a truncation boundary may flip
+    for s in (0, S - 1):
+        for ear in range(2):
+            ref, _ = oracle.fastconv(xs[s], taps[s, ear], Bk, 1, n_fft)
+            assert_i16_parity(one[s, ear], ref, 2e-3, "fastconv stream kernel")
+
+
 def test_fastconv_scene_mix(be, oracle):
     """Mode B: sources of a scene are multiply-accumulated in the frequency domain into one binaural pair."""
     p = be.L.fastconv_params("bench")
@@ -524,7 +562,7 @@ def test_pitch_dev_chunked_and_edge_inputs(be, oracle):
 
 
 @pytest.mark.parametrize("what", ["denoise_tile", "denoise_stream", "denoise_stream_ref", "pitch", "mvdr_td", "mvdr_fft", "fft4096",
-                                  "mfcc_bench", "mfcc_ref"])
+                                  "mfcc_bench", "mfcc_ref", "fastconv_stream"])
 def test_emulator_fiber_order_invariance(what, monkeypatch):
     """Missing-barrier detector for the emulated build: ascending and descending fiber schedules must agree."""
     from backends import EmulBackend
@@ -537,6 +575,17 @@ def test_emulator_fiber_order_invariance(what, monkeypatch):
     elif what == "pitch":
         x = np.stack([synth.denoise_stream(s, 9 * 512) for s in range(3)])
         run = lambda: np.concatenate([a.astype(np.float64) for a in be.ctx.pitch(x, be.L.pitch_params("ref"))], axis=1)
+    elif what == "fastconv_stream":
+        pf = be.L.fastconv_params("bench")
+        rng = np.random.default_rng(5)
+        xs = rng.integers(-4000, 4000, (3, 11 * pf.block)).astype(np.int16)
+        taps = np.zeros((3, 2, pf.n_taps)); taps[:, :, 8] = 1.0; taps[:, :, 9:80] = rng.normal(0, 0.05, (3, 2, 71))
+        def run():
+            st = be.ctx.fastconv_state(pf, 3, taps)
+            out = np.zeros((3, 2, 10 * pf.block), np.int16)
+            assert st.run(xs, 11 * pf.block, 11, out, 10 * pf.block) == 10
+            st.close()
+            return out
     elif what.startswith("mfcc"):
         p = be.L.mfcc_params(what[5:])
         n = p.frame_len + 6 * p.hop          # 7 frames: an odd count leaves the last warp step half empty at n_fft 512
