@@ -1,4 +1,5 @@
 // jdsp_conv_mfcc.cu -- C ABI (include/jdsp.h), part 3: the fast-convolution and MFCC pipelines.
+#include <algorithm>
 #include "jdsp_host.hpp"
 #include "kernels_conv_mfcc.cuh"
 #include "kernels_fastconv.cuh"
@@ -218,11 +219,10 @@ struct jdsp_mfcc_plan {
     std::vector<double> weight;  // rgdFilterBank
     std::vector<int32_t> chan;   // rgdFiBins
     // device tables of mfcc_kernel (kernels_mfcc.cuh): window, DCT x lifter, and the filterbank laid out per thread slot
-    float *d_win_half = nullptr, *d_dct = nullptr;
-    float2 *d_slot_w = nullptr;
-    uint32_t *d_slot_ctl = nullptr;
-    int *d_slot_pid = nullptr, *d_run_start = nullptr;
-    int n_pieces = 0;
+    float *d_win_half = nullptr, *d_dct = nullptr, *d_slot_w = nullptr;
+    uint32_t *d_slot_ctl = nullptr, *d_refs = nullptr;
+    int *d_slot_pid = nullptr;
+    int n_pieces = 0, lmax = 0, cpt = 0;
 };
 
 extern "C" {
@@ -246,7 +246,7 @@ int jdsp_mfcc_plan_destroy(jdsp_ctx *c, jdsp_mfcc_plan *pl) {
     REQUIRE(c, "ctx is null");
     cudaStreamSynchronize(c->stream);
     cudaFree(pl->d_win_half); cudaFree(pl->d_dct); cudaFree(pl->d_slot_w); cudaFree(pl->d_slot_ctl); cudaFree(pl->d_slot_pid);
-    cudaFree(pl->d_run_start);
+    cudaFree(pl->d_refs);
     delete pl;
     return JDSP_OK;
 }
@@ -289,32 +289,43 @@ int jdsp_mfcc_plan_create(jdsp_ctx *c, const jdsp_mfcc_params *p, jdsp_mfcc_plan
         piece[i] = id;
     }
     pl->n_pieces = piece[nbin - 1] + 1;
-    std::vector<float2> slot_w((size_t)NSLOT * G, make_float2(0.f, 0.f));
+    std::vector<float> slot_w((size_t)NSLOT * G, 0.f);
     std::vector<uint32_t> slot_ctl((size_t)G, 0u);
     std::vector<int> slot_pid((size_t)2 * G, 0), run_start((size_t)C + 3, pl->n_pieces);
-    auto share = [&](int i) { return make_float2((float)(1.0 - pl->weight[i]), (float)pl->weight[i]); };
     for (int t = 0; t < G; ++t) {
         for (int j = 0; j < KP; ++j) {
             const int lo = KP * t + j, hi = nbin - KP * t - j;
-            slot_w[(size_t)j * G + t] = share(lo);
+            slot_w[(size_t)j * G + t] = (float)pl->weight[lo];
             if (j > 0 && piece[lo] != piece[lo - 1]) slot_ctl[t] |= 1u << j;
             if (hi < nbin) {
-                slot_w[(size_t)(KP + 1 + j) * G + t] = share(hi);
+                slot_w[(size_t)(KP + 1 + j) * G + t] = (float)pl->weight[hi];
                 if (j > 0 && hi + 1 < nbin && piece[hi] != piece[hi + 1]) slot_ctl[t] |= 1u << (16 + j);
             }
         }
         slot_pid[t] = piece[KP * t];
         slot_pid[G + t] = piece[nbin - KP * t < nbin ? nbin - KP * t : nbin - 1];
     }
-    slot_w[(size_t)KP * G + (G - 1)] = share(nbin / 2);
+    slot_w[(size_t)KP * G + (G - 1)] = (float)pl->weight[nbin / 2];
     if (piece[nbin / 2] != piece[nbin / 2 - 1]) slot_ctl[G - 1] |= 1u << KP;
     for (int i = nbin - 1; i >= 0; --i) run_start[pl->chan[i]] = piece[i];   // first piece of every index that occurs ...
     for (int v = C + 1; v >= 0; --v) if (run_start[v] > run_start[v + 1]) run_start[v] = run_start[v + 1];   // ... the next one's otherwise
+    // channel c (MelFilterBank, :157-168) = the (1-w) shares of the bins of index c plus the w shares of the bins of index c+1: a
+    // fixed-length list per channel, padded with the always-zero piece n_pieces; thread t of a frame group sums channels t + G*i
+    pl->lmax = 1;
+    for (int v = 0; v <= C; ++v) pl->lmax = std::max(pl->lmax, run_start[v + 1] - run_start[v]);
+    pl->cpt = (C + G - 1) / G;
+    std::vector<uint32_t> refs((size_t)pl->cpt * pl->lmax * G, (uint32_t)pl->n_pieces * 0x10001u);
+    for (int ch = 0; ch < C; ++ch)
+        for (int l = 0; l < pl->lmax; ++l) {
+            const uint32_t u = run_start[ch] + l < run_start[ch + 1] ? run_start[ch] + l : pl->n_pieces;
+            const uint32_t v = run_start[ch + 1] + l < run_start[ch + 2] ? run_start[ch + 1] + l : pl->n_pieces;
+            refs[((size_t)(ch / G) * pl->lmax + l) * G + ch % G] = u | (v << 16);
+        }
     // M4 DCT (:176-183) times M5 lifter (:185-192)
-    std::vector<float> dct((size_t)p->n_cep * C);
+    std::vector<float> dct((size_t)C * 16, 0.f);   // [channel][cepstrum], rows padded to 16
     for (int i = 1; i <= p->n_cep; ++i) {
         const double lift = 1 + 0.5 * p->lifter * sin(p->pi_literal * i / p->lifter);
-        for (int k = 1; k <= C; ++k) dct[(size_t)(i - 1) * C + (k - 1)] = (float)(sqrt(2.0 / C) * cos(p->pi_literal * i * (k - 0.5) / (double)C) * lift);
+        for (int k = 1; k <= C; ++k) dct[(size_t)(k - 1) * 16 + (i - 1)] = (float)(sqrt(2.0 / C) * cos(p->pi_literal * i * (k - 0.5) / (double)C) * lift);
     }
     std::vector<float> wh(W);
     for (int i = 0; i < W; ++i) wh[i] = (float)(0.5 * (p->win_a0 - p->win_a1 * cos(2 * p->pi_literal * i / (W - 1))));
@@ -323,7 +334,7 @@ int jdsp_mfcc_plan_create(jdsp_ctx *c, const jdsp_mfcc_params *p, jdsp_mfcc_plan
     if (rc == JDSP_OK) rc = upload(c, slot_w, &pl->d_slot_w);
     if (rc == JDSP_OK) rc = upload(c, slot_ctl, &pl->d_slot_ctl);
     if (rc == JDSP_OK) rc = upload(c, slot_pid, &pl->d_slot_pid);
-    if (rc == JDSP_OK) rc = upload(c, run_start, &pl->d_run_start);
+    if (rc == JDSP_OK) rc = upload(c, refs, &pl->d_refs);
     if (rc != JDSP_OK) { jdsp_mfcc_plan_destroy(c, pl); return rc; }
     *out = pl;
     return JDSP_OK;
@@ -339,14 +350,16 @@ int jdsp_mfcc_plan_tables(jdsp_mfcc_plan *pl, double *weight, int32_t *chan) {
 template <int NC, int MU> static int launch_mfcc(jdsp_ctx *c, const MfccArgs &a) {
     using Geo = MfccGeom<NC>;
     auto kfn = mfcc_kernel<NC, MU>;
-    TRY(opt_in_smem(kfn, Geo::SMEM));
+    const size_t smem = Geo::smem(a.n_mel, a.n_pieces, a.lmax, a.cpt, a.xspan);
+    if (smem > 227 * 1024) return fail(JDSP_ERR_UNSUPPORTED, "MFCC: frame hop / channel count too large for the kernel's shared-memory layout");
+    TRY(opt_in_smem(kfn, smem));
     int per_sm = 4;
 #ifndef JDSP_EMUL
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, Geo::NT, Geo::SMEM));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, Geo::NT, smem));
     if (per_sm < 1) return fail(JDSP_ERR_CUDA, "MFCC kernel does not fit an SM");
 #endif
-    const long items = a.n_utts * ((a.n_frames + Geo::FPW - 1) / Geo::FPW);
-    JDSP_LAUNCH_PTR(kfn, dim3(grid_for(c, (items + Geo::NW - 1) / Geo::NW, per_sm)), dim3(Geo::NT), Geo::SMEM, c->stream, a);
+    const long batches = a.n_utts * ((a.n_frames + Geo::FB - 1) / Geo::FB);
+    JDSP_LAUNCH_PTR(kfn, dim3(grid_for(c, (batches + Geo::NW - 1) / Geo::NW, per_sm)), dim3(Geo::NT), smem, c->stream, a);
     return launch_check(c);
 }
 
@@ -369,8 +382,11 @@ int jdsp_mfcc_frames_i16_dev(jdsp_ctx *c, jdsp_mfcc_plan *pl, const int16_t *d_i
     MfccArgs a;
     a.in = d_in; a.in_pitch = in_pitch; a.n_utts = n_utts; a.n_frames = nf;
     a.feat = d_feat; a.feat_pitch = feat_pitch; a.win_half = pl->d_win_half; a.tw = (const cf *)tw; a.twr = (const float2 *)twr;
-    a.slot_w = pl->d_slot_w; a.slot_ctl = pl->d_slot_ctl; a.slot_pid = pl->d_slot_pid; a.run_start = pl->d_run_start; a.dct = pl->d_dct;
+    a.slot_w = pl->d_slot_w; a.slot_ctl = pl->d_slot_ctl; a.slot_pid = pl->d_slot_pid; a.refs = pl->d_refs; a.dct = pl->d_dct;
     a.frame_len = p.frame_len; a.hop = p.hop; a.n_mel = p.n_mel; a.n_cep = p.n_cep; a.preemph = (float)p.preemph;
+    a.n_pieces = pl->n_pieces; a.lmax = pl->lmax; a.cpt = pl->cpt;
+    // samples per PCM staging buffer: 8 in front (16-byte aligned span start), the frames of a step, n_fft behind the last frame start
+    a.xspan = 8 + (NC == 256 ? p.hop : 0) + p.n_fft + 24;
     // packed points t + G*m, m >= MU, lie past frame_len for every thread: the 13-row instance covers frames of up to 13*n_fft/32
     // samples (the bench preset's 400 of 512)
     if (NC == 256) return p.frame_len <= 13 * 32 ? launch_mfcc<256, 13>(c, a) : launch_mfcc<256, 16>(c, a);

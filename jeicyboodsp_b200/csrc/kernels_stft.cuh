@@ -60,6 +60,34 @@ JDSP_DEV void retangle2x(cf Y1, cf Y2, float c, float s, cf &Zk, cf &Zmk) {
     Zmk = c2(__ffma2_rn(make_float2(Pv.y, Pv.x), make_float2(1.f, 1.f), make_float2(Sv.x, -Sv.y)));
 }
 
+// (cos, sin)(theta + 2*pi*M/32) from (cos, sin)(theta): the post-twiddle of bin t + G*m from the thread's own seed
+template <int M> JDSP_DEV float2 rot32(float2 cs) {
+    if constexpr (M == 0) return cs;
+    else {
+        constexpr double C[8] = {1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708, 0.70710678118654752440,
+                                 0.55557023301960222474, 0.38268343236508977173, 0.19509032201612826785};
+        constexpr double S[8] = {0.0, 0.19509032201612826785, 0.38268343236508977173, 0.55557023301960222474, 0.70710678118654752440,
+                                 0.83146961230254523708, 0.92387953251128675613, 0.98078528040323044913};
+        const float c = (float)C[M], s = (float)S[M];
+        return __ffma2_rn(cs, make_float2(c, c), __fmul2_rn(make_float2(cs.y, cs.x), make_float2(-s, s)));
+    }
+}
+
+// post-twiddle (cos, sin)(2*pi*(t + G*m)/N) of a thread's m-th bin from its seed (cos, sin)(2*pi*t/N); G/N = 1/32 for the
+// 16-points-per-thread groups.  m must be a compile-time constant after unrolling.
+JDSP_DEV float2 post_twiddle(float2 wt, int m) {
+    switch (m) {
+        case 0: return wt;
+        case 1: return rot32<1>(wt);
+        case 2: return rot32<2>(wt);
+        case 3: return rot32<3>(wt);
+        case 4: return rot32<4>(wt);
+        case 5: return rot32<5>(wt);
+        case 6: return rot32<6>(wt);
+        default: return rot32<7>(wt);
+    }
+}
+
 // ================================================================================================
 // Round trip.  Two consecutive blocks of one stream ride one complex transform (block b in the real
 // lane, block b+1 in the imaginary lane); FFT followed by IFFT is linear, so the lanes never mix.
