@@ -34,14 +34,6 @@ struct FastconvStreamGeom {
     static_assert(G == 16 || G == 32, "a source group is a half warp or a warp");
 };
 
-// 64-bit shuffle within a group of G lanes
-template <int G> JDSP_DEV cf shfl_cf(cf v, int src) {
-    cf r;
-    r.x = __shfl_sync(0xffffffffu, v.x, src, G);
-    r.y = __shfl_sync(0xffffffffu, v.y, src, G);
-    return r;
-}
-
 // 512-point transform (passes 16 x 16 x 2, 16 points per thread, 32 threads) with every twiddle rebuilt from thread constants: the
 // second pass needs W_256^(i k), i = 1..15, k = t mod 16 -- four seeds (i = 1, 2, 4, 8) and 11 products of depth <= 3; the third
 // W_512^(t + 32 u) = W_512^t * W_16^u with W_16^u a compile-time constant.  The tables cost 46 shared-memory wavefronts per
@@ -190,11 +182,12 @@ __global__ void __launch_bounds__(FastconvStreamGeom<NC>::NT, 4) fastconv_stream
             fastconv_fft<NC, false>(reg, t, ebuf, tw, sd);
             // ---- real spectrum of this thread's bin pairs (k, NC-k), k = t + G*m: the mirrored bin lives in the partner thread
             cf X1[HM], X2[HM], XS;
+            const float2 wtb = opaque(wt);
 #pragma unroll
             for (int m = 0; m < HM; ++m) {
                 cf Bm = shfl_cf<G>(reg[E - 1 - m], partner);
                 if (t == 0) Bm = (m == 0) ? reg[0] : reg[E - m];     // thread 0 pairs with itself: bin NC - G*m is its own point E - m
-                const float2 cs = post_twiddle(wt, m);
+                const float2 cs = post_twiddle(wtb, m);
                 untangle2x(reg[m], Bm, cs.x, cs.y, X1[m], X2[m]);
             }
             {
@@ -216,7 +209,7 @@ __global__ void __launch_bounds__(FastconvStreamGeom<NC>::NT, 4) fastconv_stream
 #pragma unroll
                 for (int m = HM - 1; m >= 0; --m) {
                     const cf h1 = fa[m * G], h2 = fb[m * G];
-                    const float2 cs = post_twiddle(wt, m);
+                    const float2 cs = post_twiddle(opaque(wtb), m);
                     const cf Y1 = cmulw(X1[m], h1.x, h1.y), Y2 = cmulw(X2[m], h2.x, h2.y);
                     cf zm;
                     retangle2x(Y1, Y2, cs.x, cs.y, reg[m], zm);

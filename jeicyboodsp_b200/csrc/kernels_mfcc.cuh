@@ -188,13 +188,14 @@ __global__ void __launch_bounds__(MfccGeom<NC>::NT, 4) mfcc_kernel(MfccArgs a) {
         group_fft<float, NC, E, false, 0>(reg, t, buf, tw);
         group_sync<0>();       // the last pass has been read out of the exchange buffer: it now takes the magnitudes
         // ---- |X| (:218-220) of the thread's bin pairs (k, NC-k), k = t + G*m; the mirrored bin lives in the partner thread -----
+        const float2 wtb = opaque(wt);
 #pragma unroll
         for (int m = 0; m < HM; ++m) {
             cf Bm;
             Bm.x = __shfl_sync(0xffffffffu, reg[E - 1 - m].x, partner, G);
             Bm.y = __shfl_sync(0xffffffffu, reg[E - 1 - m].y, partner, G);
             if (t == 0) Bm = (m == 0) ? reg[0] : reg[E - m];     // thread 0 pairs with itself: bin NC - G*m is its own point E - m
-            const float2 cs = post_twiddle(wt, m);
+            const float2 cs = post_twiddle(wtb, m);
             cf X1, X2;
             untangle2x(reg[m], Bm, cs.x, cs.y, X1, X2);
             mag_own[m * MSTRIDE] = sqrt_fast(X1.x * X1.x + X1.y * X1.y);
