@@ -29,70 +29,16 @@ struct FastconvStreamGeom {
     static constexpr size_t OFF_FB = OFF_FA + (size_t)2 * HM * G * sizeof(cf);                        // [2][HM][G] H[NC-k]
     static constexpr size_t OFF_FS = OFF_FB + (size_t)2 * HM * G * sizeof(cf);                        // [2] H[NC/2]
     static constexpr size_t OFF_TW = OFF_FS + 2 * sizeof(cf);
-    static constexpr size_t OFF_RING = (OFF_TW + (size_t)NTW * sizeof(cf) + 15) & ~(size_t)15;       // [3][HM][NT] words
+    static constexpr size_t OFF_TWR = (OFF_TW + (size_t)NTW * sizeof(cf) + 15) & ~(size_t)15;
+    static constexpr size_t OFF_RING = OFF_TWR + (size_t)(NC / 2 + 2) * sizeof(float2);               // [3][HM][NT] words
     static constexpr size_t SMEM = OFF_RING + (size_t)3 * HM * NT * sizeof(uint32_t);
     static_assert(G == 16 || G == 32, "a source group is a half warp or a warp");
 };
 
-// 512-point transform (passes 16 x 16 x 2, 16 points per thread, 32 threads) with every twiddle rebuilt from thread constants: the
-// second pass needs W_256^(i k), i = 1..15, k = t mod 16 -- four seeds (i = 1, 2, 4, 8) and 11 products of depth <= 3; the third
-// W_512^(t + 32 u) = W_512^t * W_16^u with W_16^u a compile-time constant.  The tables cost 46 shared-memory wavefronts per
-// transform (21 % of this kernel's shared-memory traffic, which runs at 87 % of the pipe: ncu, profiles/round2); the rebuild costs
-// ~15 more packed instructions.  Same pass structure and exchange layout as group_fft<float, 512, 16>.
-struct Fft512Seeds { cf w1, w2, w4, w8, w3; };
-JDSP_DEV Fft512Seeds fft512_seeds(int t, const cf *__restrict__ tw) {
-    using TL = TwLayout<512, 16>;
-    const cf *p2 = tw + TL::offset(16) + (t & 15);
-    Fft512Seeds s;
-    s.w1 = p2[0]; s.w2 = p2[16]; s.w4 = p2[3 * 16]; s.w8 = p2[7 * 16];
-    s.w3 = tw[TL::offset(256) + t];
-    return s;
-}
-template <bool INV> JDSP_DEV void fft512_seeded(cf (&reg)[16], int t, cf *buf, const Fft512Seeds &sd) {
-    constexpr int NC = 512, E = 16;
-    dftR<E, INV>(reg);
-    fft_pass_store<float, NC, E, 16, 1>(reg, t, buf);
-    group_sync<0>();
-    fft_load_regs<float, NC, E>(reg, t, buf);
-    {
-        const cf w1 = sd.w1, w2 = sd.w2, w4 = sd.w4, w8 = sd.w8;
-        reg[1] = cmul<INV>(reg[1], w1); reg[2] = cmul<INV>(reg[2], w2); reg[4] = cmul<INV>(reg[4], w4); reg[8] = cmul<INV>(reg[8], w8);
-        const cf w3 = cmul<false>(w1, w2), w5 = cmul<false>(w1, w4), w6 = cmul<false>(w2, w4);
-        reg[3] = cmul<INV>(reg[3], w3); reg[5] = cmul<INV>(reg[5], w5); reg[6] = cmul<INV>(reg[6], w6);
-        const cf w7 = cmul<false>(w3, w4);
-        reg[7] = cmul<INV>(reg[7], w7);
-        reg[9] = cmul<INV>(reg[9], cmul<false>(w1, w8));
-        reg[10] = cmul<INV>(reg[10], cmul<false>(w2, w8));
-        reg[11] = cmul<INV>(reg[11], cmul<false>(w3, w8));
-        reg[12] = cmul<INV>(reg[12], cmul<false>(w4, w8));
-        reg[13] = cmul<INV>(reg[13], cmul<false>(w5, w8));
-        reg[14] = cmul<INV>(reg[14], cmul<false>(w6, w8));
-        reg[15] = cmul<INV>(reg[15], cmul<false>(w7, w8));
-    }
-    dftR<E, INV>(reg);
-    group_sync<0>();
-    fft_pass_store<float, NC, E, 16, 16>(reg, t, buf);
-    group_sync<0>();
-    fft_load_regs<float, NC, E>(reg, t, buf);
-    // third pass, radix 2: element t + 32 u pairs with t + 32 u + 256 (both this thread's), twiddle W_512^(t + 32 u)
-    {
-        const cf w = sd.w3;
-        cf v;
-        v = cmul<INV>(reg[8], w); reg[8] = csub(reg[0], v); reg[0] = cadd(reg[0], v);
-        v = cmul<INV>(reg[9], cw16<false, 1>(w)); reg[9] = csub(reg[1], v); reg[1] = cadd(reg[1], v);
-        v = cmul<INV>(reg[10], cw16<false, 2>(w)); reg[10] = csub(reg[2], v); reg[2] = cadd(reg[2], v);
-        v = cmul<INV>(reg[11], cw16<false, 3>(w)); reg[11] = csub(reg[3], v); reg[3] = cadd(reg[3], v);
-        v = cmul<INV>(reg[12], cw16<false, 4>(w)); reg[12] = csub(reg[4], v); reg[4] = cadd(reg[4], v);
-        v = cmul<INV>(reg[13], cw16<false, 5>(w)); reg[13] = csub(reg[5], v); reg[5] = cadd(reg[5], v);
-        v = cmul<INV>(reg[14], cw16<false, 6>(w)); reg[14] = csub(reg[6], v); reg[6] = cadd(reg[6], v);
-        v = cmul<INV>(reg[15], cw16<false, 7>(w)); reg[15] = csub(reg[7], v); reg[7] = cadd(reg[7], v);
-    }
-}
-template <int NC, bool INV> JDSP_DEV void fastconv_fft(cf (&reg)[16], int t, cf *buf, const cf *tw, const Fft512Seeds &sd) {
-    if constexpr (NC == 512) fft512_seeded<INV>(reg, t, buf, sd);
-    else group_fft<float, NC, 16, INV, 0>(reg, t, buf, tw);
-}
-
+// (Round 2 measured the twiddles of the 512-point transform and the post-twiddles rebuilt from per-thread seeds instead of the
+// shared-memory tables: 24 % fewer shared-memory wavefronts, ~190 more packed instructions per block and 68 bytes of spills --
+// 43.8 ms against 43.0 ms: the kernel is bound by issue slots and the fp32 pipe (packed arithmetic is 52 % of its instructions),
+// not by the shared-memory pipe, so the tables stay.)
 template <int NC>
 __global__ void __launch_bounds__(FastconvStreamGeom<NC>::NT, 4) fastconv_stream_kernel(FastconvArgs a) {
     using Geo = FastconvStreamGeom<NC>;
@@ -103,6 +49,7 @@ __global__ void __launch_bounds__(FastconvStreamGeom<NC>::NT, 4) fastconv_stream
     cf *filtB = reinterpret_cast<cf *>(smem_raw + Geo::OFF_FB);
     cf *filtS = reinterpret_cast<cf *>(smem_raw + Geo::OFF_FS);
     cf *tw = reinterpret_cast<cf *>(smem_raw + Geo::OFF_TW);
+    float2 *twr = reinterpret_cast<float2 *>(smem_raw + Geo::OFF_TWR);
     uint32_t *ring = reinterpret_cast<uint32_t *>(smem_raw + Geo::OFF_RING) + threadIdx.x;
 
     const int tid = threadIdx.x, gi = tid / G, t = tid % G;
@@ -111,11 +58,11 @@ __global__ void __launch_bounds__(FastconvStreamGeom<NC>::NT, 4) fastconv_stream
     const long skip = seen0 < 1 ? 1 - seen0 : 0;      // the very first block of a source emits nothing and counts as zeros (:118-123)
     const bool want_f32 = a.out_f32 != nullptr;
     for (int i = tid; i < Geo::NTW; i += NT) tw[i] = a.tw[i];
+    for (int i = tid; i <= NC / 2; i += NT) twr[i] = a.twr[i];
 
     cf *ebuf = ebufs + gi * PADN;
-    const float2 wt = a.twr[t], cs_half = a.twr[NC / 2];   // post-twiddle of bin t + G*m = the thread's seed turned by 2*pi*m/32
-    Fft512Seeds sd;
-    if constexpr (NC == 512) sd = fft512_seeds(t, a.tw);
+    const float2 *twr_t = twr + t;
+    const float2 cs_half = a.twr[NC / 2];
     const int partner = (G - t) & (G - 1);
     // time slices: group gi walks blocks [gi*L, gi*L + L); every group runs L steps so that the halves of a warp stay in step
     const long L = (n_blocks + NGRP - 1) / NGRP;
@@ -179,15 +126,14 @@ __global__ void __launch_bounds__(FastconvStreamGeom<NC>::NT, 4) fastconv_stream
                 reg[m] = c2(s16x2_to_f32(wp[m]));
                 reg[m + HM] = c2(s16x2_to_f32(wc[m]));
             }
-            fastconv_fft<NC, false>(reg, t, ebuf, tw, sd);
+            group_fft<float, NC, E, false, 0>(reg, t, ebuf, tw);
             // ---- real spectrum of this thread's bin pairs (k, NC-k), k = t + G*m: the mirrored bin lives in the partner thread
             cf X1[HM], X2[HM], XS;
-            const float2 wtb = opaque(wt);
 #pragma unroll
             for (int m = 0; m < HM; ++m) {
                 cf Bm = shfl_cf<G>(reg[E - 1 - m], partner);
                 if (t == 0) Bm = (m == 0) ? reg[0] : reg[E - m];     // thread 0 pairs with itself: bin NC - G*m is its own point E - m
-                const float2 cs = post_twiddle(wtb, m);
+                const float2 cs = twr_t[G * m];
                 untangle2x(reg[m], Bm, cs.x, cs.y, X1[m], X2[m]);
             }
             {
@@ -209,7 +155,7 @@ __global__ void __launch_bounds__(FastconvStreamGeom<NC>::NT, 4) fastconv_stream
 #pragma unroll
                 for (int m = HM - 1; m >= 0; --m) {
                     const cf h1 = fa[m * G], h2 = fb[m * G];
-                    const float2 cs = post_twiddle(opaque(wtb), m);
+                    const float2 cs = twr_t[G * m];
                     const cf Y1 = cmulw(X1[m], h1.x, h1.y), Y2 = cmulw(X2[m], h2.x, h2.y);
                     cf zm;
                     retangle2x(Y1, Y2, cs.x, cs.y, reg[m], zm);
@@ -218,7 +164,7 @@ __global__ void __launch_bounds__(FastconvStreamGeom<NC>::NT, 4) fastconv_stream
                     carry = zm;
                 }
                 group_sync<0>();      // the exchange buffer: everybody is past the previous transform's last loads
-                fastconv_fft<NC, true>(reg, t, ebuf, tw, sd);
+                group_fft<float, NC, E, true, 0>(reg, t, ebuf, tw);
                 // ---- out[i] = (short) y[i + n_taps - 1] (:156-158): the last B samples of the window = points HM.. of every thread
                 if (valid && blk >= 0) {
                     uint32_t *op = reinterpret_cast<uint32_t *>(a.out + (src * NE + ear) * out_pitch) + blk * (B / 2) + t;

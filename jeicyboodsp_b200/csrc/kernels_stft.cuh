@@ -96,20 +96,6 @@ JDSP_DEV float2 opaque(float2 v) {
 #endif
     return v;
 }
-// the same with a run-time m (tables built once per stream)
-JDSP_DEV float2 post_twiddle_rt(float2 wt, int m) {
-    switch (m) {
-        case 0: return post_twiddle(wt, 0);
-        case 1: return post_twiddle(wt, 1);
-        case 2: return post_twiddle(wt, 2);
-        case 3: return post_twiddle(wt, 3);
-        case 4: return post_twiddle(wt, 4);
-        case 5: return post_twiddle(wt, 5);
-        case 6: return post_twiddle(wt, 6);
-        default: return post_twiddle(wt, 7);
-    }
-}
-
 // ================================================================================================
 // Round trip.  Two consecutive blocks of one stream ride one complex transform (block b in the real
 // lane, block b+1 in the imaginary lane); FFT followed by IFFT is linear, so the lanes never mix.
@@ -341,10 +327,7 @@ __global__ void __launch_bounds__(DenoiseGeom<NC, F>::NT, NC == 256 ? 6 : 3) den
                 const float n1 = ns[k], n2 = ns[NC - k];
                 nss1[q] = (MODE == 0 ? n1 : n1 * n1) * inv_n;
                 nss2[q] = (MODE == 0 ? n2 : n2 * n2) * inv_n;
-                // the same arithmetic as the stream-group kernel (seed of thread k mod G turned by 2*pi*(k / G)/32), so that the two
-                // kernels agree bit for bit; bin NC/2 has its own table entry in both
-                constexpr int GS = NC / 16;
-                const float2 w = (k == NC / 2) ? a.twr[k] : post_twiddle_rt(a.twr[k % GS], k / GS);
+                const float2 w = a.twr[k];
                 tc[q] = w.x; ts[q] = w.y;
             }
         }

@@ -11,6 +11,9 @@
 //   * the per-bin stage works on the transform's own registers: bins k < NC/2 stay with their thread, the
 //     mirrored bins NC-k come from / go back to the partner thread through one small shared-memory exchange.
 // Shared memory carries only the Stockham exchange of each transform, that mirror exchange, and the tables.
+// (Round 2 measured the mirror exchange by shuffles and the post-twiddles rebuilt from a per-thread seed instead of the table:
+// 13 % fewer shared-memory wavefronts, ~4 % more packed arithmetic, 20-40 bytes of spills at the 128-register cap -- 9 % SLOWER,
+// 17.8 / 18.7 ms against 16.3 / 16.8 ms per pass; the kernel is bound by issue slots and the fp32 pipe, not by shared memory.)
 #pragma once
 #include "kernels_stft.cuh"
 
@@ -29,13 +32,15 @@ struct StreamGeom {
     // the shared-memory pipe at 64-75 %), so off.
     static constexpr bool SEED_TW = false;
     static constexpr int PADN = padded_len(NC);
-    static constexpr int GBUF = PADN + 1;                 // odd pitch: the groups of a warp start in different banks
+    static constexpr int GBUF = PADN + 1;                 // slot PADN mirrors bin 0 ("bin NC")
     static constexpr int NTW = TwLayout<NC, E>::total;
+    static constexpr int NTWR = NC / 2 + 2;               // (cos, sin) per bin pair, padded to an even count
     static constexpr size_t OFF_FBUF = 0;
     static constexpr size_t OFF_WVAD = (OFF_FBUF + (size_t)GPC * GBUF * sizeof(cf) + 15) & ~(size_t)15;
     static constexpr size_t OFF_TW = OFF_WVAD + (size_t)H * sizeof(double);
     static constexpr size_t OFF_WIN = (OFF_TW + (size_t)NTW * sizeof(cf) + 15) & ~(size_t)15;
-    static constexpr size_t OFF_AVG = OFF_WIN + (size_t)N * sizeof(float);                // noise averages (avg[k], avg[NC-k]) [m][thread]
+    static constexpr size_t OFF_TWR = OFF_WIN + (size_t)N * sizeof(float);
+    static constexpr size_t OFF_AVG = OFF_TWR + (size_t)NTWR * sizeof(float2);            // noise averages (avg[k], avg[NC-k]) [m][thread]
     static constexpr size_t OFF_PCM = OFF_AVG + (size_t)(E / 2) * NT * sizeof(float2);    // next block, two buffers of [m][thread] words
     static constexpr size_t SMEM = OFF_PCM + (size_t)2 * (E / 2) * NT * sizeof(uint32_t);
     static_assert(G == 16 || G == 32, "a stream group is a half warp or a warp");
@@ -63,18 +68,13 @@ template <int G> JDSP_DEV cf shfl_cf(cf v, int src) {
     return r;
 }
 
-// Per-bin stage of one frame on the transform's own registers: bins k = t + G*m (m < 8) pair with NC-k, which is point E-1-m of
-// the partner thread G-t (thread 0 pairs with itself: bin NC - G*m is its own point E-m, "bin NC" its point 0) and travels by two
-// shuffles each way -- a store + load through shared memory costs twice the data-pipe cycles (profiles/microbench/mb3.txt) and two
-// group syncs.  Bin NC/2 (thread 0, m = 8) pairs with itself and goes through the very same formulas as in the CTA-per-stream
-// kernel (A = B, second output kept), so that the two kernels agree bit for bit; so do the post-twiddles, which both kernels turn
-// out of the thread's seed (post_twiddle).
-template <int MODE, bool UPD, int E, int G, int NT>
-JDSP_DEV void denoise_bins(cf (&reg)[E], int t, float2 wt, float2 cs_half, unsigned cbits, float inv_n,
+// Per-bin stage of one frame on the transform's own registers: bins k = t + G*m (m < 8) pair with NC-k held by the partner
+// thread (exchanged through mir[]); bin NC/2 (thread 0, m = 8) pairs with itself and goes through the very same formulas as
+// in the CTA-per-stream kernel (A = B, second output kept), so that the two kernels agree bit for bit.
+template <int MODE, bool UPD, int E, int G, int MSTRIDE, int NT>
+JDSP_DEV void denoise_bins(cf (&reg)[E], cf *mir, const float2 *twr_t, float2 cs_half, unsigned cbits, float inv_n,
                            float2 *avgp, float (&nss1)[E / 2], float (&nss2)[E / 2], float &avgS, float &nssS) {
     constexpr int HM = E / 2, U = UPD ? 1 : 0;
-    const int partner = (G - t) & (G - 1);
-    cf carry;      // thread 0: the mirrored output of its previous (higher) pair, which is its own point E-1-m
     {
         cf X1, X2;
         untangle2x(reg[HM], reg[HM], cs_half.x, cs_half.y, X1, X2);
@@ -82,17 +82,13 @@ JDSP_DEV void denoise_bins(cf (&reg)[E], int t, float2 wt, float2 cs_half, unsig
         const cf Y1 = denoise_bin<MODE, U>(X1, cbits, inv_n, avgS, nssS);
         const cf Y2 = denoise_bin<MODE, U>(X2, cbits, inv_n, a2, n2);
         cf Zk;
-        retangle2x(Y1, Y2, cs_half.x, cs_half.y, Zk, carry);
+        retangle2x(Y1, Y2, cs_half.x, cs_half.y, Zk, reg[HM]);
     }
-    // descending m: point E-1-m is read (as the partner's mirrored bin) in the step that overwrites it, the points thread 0 reads
-    // instead (E-m) are overwritten one step later
 #pragma unroll
-    for (int m = HM - 1; m >= 0; --m) {
-        cf Bm = shfl_cf<G>(reg[E - 1 - m], partner);
-        if (t == 0) Bm = (m == 0) ? reg[0] : reg[E - m];
-        const float2 cs = post_twiddle(wt, m);
+    for (int m = 0; m < HM; ++m) {
+        const float2 cs = twr_t[G * m];
         cf X1, X2;
-        untangle2x(reg[m], Bm, cs.x, cs.y, X1, X2);
+        untangle2x(reg[m], mir[-m * MSTRIDE], cs.x, cs.y, X1, X2);
         float2 av = make_float2(0.f, 0.f);
         if (UPD) av = avgp[m * NT];          // the averages live in shared memory: only noise blocks touch them
         const cf Y1 = denoise_bin<MODE, U>(X1, cbits, inv_n, av.x, nss1[m]);
@@ -100,9 +96,7 @@ JDSP_DEV void denoise_bins(cf (&reg)[E], int t, float2 wt, float2 cs_half, unsig
         if (UPD) avgp[m * NT] = av;
         cf Zm;
         retangle2x(Y1, Y2, cs.x, cs.y, reg[m], Zm);
-        const cf v = shfl_cf<G>(Zm, partner);
-        reg[E - 1 - m] = (t == 0) ? carry : v;
-        carry = Zm;
+        mir[-m * MSTRIDE] = Zm;
     }
 }
 
@@ -110,11 +104,13 @@ template <int NC, int MODE, int E_ = 16>
 __global__ void __maxnreg__((StreamGeom<NC, E_>::MAXREG)) denoise_stream_kernel(DenoiseArgs a) {
     using Geo = StreamGeom<NC, E_>;
     constexpr int N = Geo::N, H = Geo::H, E = Geo::E, G = Geo::G, NT = Geo::NT, GPC = Geo::GPC, HM = E / 2;
+    constexpr int MSTRIDE = G + G / 16;                   // padded distance between a thread's consecutive points
     JDSP_DYN_SMEM(smem_raw);
     cf *fbuf = reinterpret_cast<cf *>(smem_raw + Geo::OFF_FBUF);
     double *wvad = reinterpret_cast<double *>(smem_raw + Geo::OFF_WVAD);
     cf *tw = reinterpret_cast<cf *>(smem_raw + Geo::OFF_TW);
     float *winh = reinterpret_cast<float *>(smem_raw + Geo::OFF_WIN);
+    float2 *twr = reinterpret_cast<float2 *>(smem_raw + Geo::OFF_TWR);
     float2 *avgp = reinterpret_cast<float2 *>(smem_raw + Geo::OFF_AVG) + threadIdx.x;
     uint32_t *pcmw = reinterpret_cast<uint32_t *>(smem_raw + Geo::OFF_PCM) + threadIdx.x;
 
@@ -122,6 +118,7 @@ __global__ void __maxnreg__((StreamGeom<NC, E_>::MAXREG)) denoise_stream_kernel(
     for (int i = tid; i < H; i += NT) wvad[i] = a.win_vad[i];
     for (int i = tid; i < Geo::NTW; i += NT) tw[i] = a.tw[i];
     for (int i = tid; i < N; i += NT) winh[i] = a.win_half[i];
+    for (int i = tid; i <= NC / 2; i += NT) twr[i] = a.twr[i];
     __syncthreads();
 
     const long n_streams = a.n_streams;
@@ -137,9 +134,11 @@ __global__ void __maxnreg__((StreamGeom<NC, E_>::MAXREG)) denoise_stream_kernel(
     const bool want_f32 = a.out_f32 != nullptr && live, want_vad = a.vad != nullptr && live;
 
     cf *buf = fbuf + g * Geo::GBUF;
+    cf *own = buf + pad16(t);                  // point t + G*m at own[m * MSTRIDE]
+    cf *mir = buf + pad16(NC - t);             // point NC - (t + G*m) at mir[-m * MSTRIDE]; slot PADN stands in for "bin NC" = bin 0
     const float2 *win2 = reinterpret_cast<const float2 *>(winh) + t;
     const double2 *wv2 = reinterpret_cast<const double2 *>(wvad) + t;
-    const float2 wt = a.twr[t], cs_half = a.twr[NC / 2];   // post-twiddle seeds: bin t + G*m turns wt by 2*pi*m/32
+    const float2 *twr_t = twr + t;
 
     // ---- the stream's carry state ---------------------------------------------------------------------------
     const long seen0 = a.st_seen[s];
@@ -242,10 +241,22 @@ __global__ void __maxnreg__((StreamGeom<NC, E_>::MAXREG)) denoise_stream_kernel(
         if constexpr (Geo::SEED_TW && NC == E * E && E == 16) group_fft_seedtw<float, NC, E, false, 0>(reg, t, buf, tw);
         else group_fft<float, NC, E, false, 0>(reg, t, buf, tw);
         // ---- per-bin stage ------------------------------------------------------------------------------------
-        const float2 wtb = opaque(wt);
-        if (cbits) denoise_bins<MODE, true, E, G, NT>(reg, t, wtb, cs_half, cbits, inv_n, avgp, nss1, nss2, avgS, nssS);
-        else denoise_bins<MODE, false, E, G, NT>(reg, t, wtb, cs_half, cbits, inv_n, avgp, nss1, nss2, avgS, nssS);
-        group_sync<0>();      // the exchange buffer: everybody is past the forward transform's last loads
+        group_sync<0>();
+#pragma unroll
+        for (int m = HM; m < E; ++m) own[m * MSTRIDE] = reg[m];
+        if (t == 0) buf[Geo::PADN] = reg[0];
+        group_sync<0>();
+        const float2 cs_half = twr[NC / 2];
+        if (cbits) denoise_bins<MODE, true, E, G, MSTRIDE, NT>(reg, mir, twr_t, cs_half, cbits, inv_n, avgp, nss1, nss2, avgS, nssS);
+        else denoise_bins<MODE, false, E, G, MSTRIDE, NT>(reg, mir, twr_t, cs_half, cbits, inv_n, avgp, nss1, nss2, avgS, nssS);
+        group_sync<0>();
+#pragma unroll
+        for (int m = HM + 1; m < E; ++m) reg[m] = own[m * MSTRIDE];
+        {
+            const cf z8 = own[HM * MSTRIDE];
+            if (t != 0) reg[HM] = z8;
+        }
+        group_sync<0>();
         // ---- inverse transform, overlap-add (:248-256), (short) cast (:252) ---------------------------------------
         if constexpr (Geo::SEED_TW && NC == E * E && E == 16) group_fft_seedtw<float, NC, E, true, 0>(reg, t, buf, tw);
         else group_fft<float, NC, E, true, 0>(reg, t, buf, tw);
