@@ -141,6 +141,22 @@ static int launch_c2c_split2(jdsp_ctx *c, const cx<float> *in, cx<float> *out, l
     return launch_check(c);
 }
 
+#ifndef JDSP_EMUL
+// N = 32768 on 2-CTA clusters (JDSP_FFT_NO_CLUSTER=1 falls back to the L2-paired split kernel)
+template <int M, bool INV>
+static int launch_c2c_cluster2(jdsp_ctx *c, const cx<float> *in, cx<float> *out, long batch) {
+    using Geo = FftCluster2Geom<M>;
+    void *t32, *twN;
+    TRY(get_table(c, 6, M, &t32));
+    TRY(get_table(c, 3, 2 * M, &twN));
+    auto kfn = fft_c2c_cluster2_kernel<M, INV>;
+    TRY(opt_in_smem(kfn, Geo::SMEM));
+    const unsigned grid = (unsigned)std::max<long>(2, std::min<long>(2 * batch, (long)(c->sm_count & ~1)));
+    kfn<<<dim3(grid), dim3(Geo::THREADS), Geo::SMEM, c->stream>>>(in, out, batch, (const cx<float> *)t32, (const cx<float> *)twN, 1.0f);
+    return launch_check(c);
+}
+#endif
+
 template <typename T, int N1, int N2, bool INV>
 static int launch_c2c_fourstep(jdsp_ctx *c, const cx<T> *in, cx<T> *out, long batch, int tkind) {
     // 256-thread CTAs (3 per SM at 80 registers): the four barriers of a tile stall 8 warps instead of 16 and more tiles
@@ -238,6 +254,9 @@ static int fft_dispatch(jdsp_ctx *c, const cx<T> *in, cx<T> *out, int n, long ba
             if constexpr (sizeof(T) == 4) { if (getenv("JDSP_FFT_FUSED")) return launch_c2c_fused<64, 256, INV>(c, in, out, batch); }
             return launch_c2c_fourstep<T, 64, 256, INV>(c, in, out, batch, tkind);
         case 32768:
+#ifndef JDSP_EMUL
+            if constexpr (sizeof(T) == 4) { if (!getenv("JDSP_FFT_NO_CLUSTER") && !getenv("JDSP_FFT_NO_SPLIT") && !getenv("JDSP_FFT_FUSED")) return launch_c2c_cluster2<16384, INV>(c, (const cx<float> *)in, (cx<float> *)out, batch); }
+#endif
             if constexpr (sizeof(T) == 4) { if (!getenv("JDSP_FFT_NO_SPLIT") && !getenv("JDSP_FFT_FUSED")) return launch_c2c_split2<16384, INV>(c, (const cx<float> *)in, (cx<float> *)out, batch); }
             if constexpr (sizeof(T) == 4) { if (getenv("JDSP_FFT_FUSED")) return launch_c2c_fused<128, 256, INV>(c, in, out, batch); }
             return launch_c2c_fourstep<T, 128, 256, INV>(c, in, out, batch, tkind);

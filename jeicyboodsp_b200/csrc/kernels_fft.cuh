@@ -266,6 +266,102 @@ fft_c2c_split2_kernel(const cx<float> *__restrict__ in, cx<float> *__restrict__ 
     }
 }
 
+#ifndef JDSP_EMUL
+// ---- N = 2 M, M = 16384, as a 2-CTA thread-block cluster: the split of fft_c2c_split2_kernel, but the two halves of a transform
+// sit on the two CTAs of one cluster and swap half of their results through distributed shared memory, so that every thread
+// writes the PAIR (X[2k], X[2k+1]) as one 16-byte store instead of every other 8 bytes (split2's stores leave 16 half-written
+// sectors per warp instruction: the load/store unit, not HBM, paced that kernel -- lg_throttle 6.4 per issue).
+//   CTA r computes Y_r[k] = X[2k + r], k < M; thread t holds k = t + G*m, m < 32.  CTA 0 keeps k < M/2 (m < 16) and ships its upper
+//   half to CTA 1, CTA 1 the reverse: 64 KB each way per transform, written straight from registers into the peer's receive
+//   buffer (st.shared::cluster), one cluster barrier later both CTAs write 16 x 512 contiguous 16-byte pairs.
+JDSP_DEV unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+JDSP_DEV unsigned map_to_cta(const void *smem_ptr, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"((unsigned)__cvta_generic_to_shared(smem_ptr)), "r"(rank));
+    return r;
+}
+JDSP_DEV void st_cluster(unsigned addr, cx<float> v) { asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory"); }
+JDSP_DEV void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+JDSP_DEV void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+template <int M> struct FftCluster2Geom {
+    static constexpr int E = 32, G = M / E, THREADS = G, N = 2 * M;
+    static constexpr int PADN = padded_len_e<E>(M);
+    static constexpr size_t OFF_RECV = ((size_t)PADN * sizeof(cx<float>) + 15) & ~(size_t)15;
+    static constexpr size_t SMEM = OFF_RECV + (size_t)(M / 2) * sizeof(cx<float>);
+};
+template <int M, bool INV>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FftCluster2Geom<M>::THREADS, 1)
+fft_c2c_cluster2_kernel(const cx<float> *__restrict__ in, cx<float> *__restrict__ out, long batch, const cx<float> *__restrict__ tw,
+                        const cx<float> *__restrict__ twN, float scale) {
+    using Geo = FftCluster2Geom<M>;
+    constexpr int E = Geo::E, G = Geo::G, N = Geo::N, HE = E / 2;
+    JDSP_DYN_SMEM(smem_raw);
+    cx<float> *exch = reinterpret_cast<cx<float> *>(smem_raw);
+    cx<float> *recv = reinterpret_cast<cx<float> *>(smem_raw + Geo::OFF_RECV);
+    const int t = threadIdx.x;
+    const unsigned r = cluster_ctarank();
+    const unsigned peer_recv = map_to_cta(recv + t, r ^ 1u);      // this thread's column of the peer's receive buffer
+    const cx<float> wt = twN[t];                                   // W_N^t
+    const long n_pairs = gridDim.x / 2;
+    bool first = true;
+    for (long f = blockIdx.x / 2; f < batch; f += n_pairs) {
+        cx<float> reg[E];
+        const cx<float> *src = in + f * N + t;
+#pragma unroll
+        for (int m = 0; m < E; ++m) reg[m] = src[G * m];
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+            const cx<float> hi = src[M + G * m];
+            if (r == 0) {
+                reg[m] = cadd(reg[m], hi);
+            } else {
+                const cx<float> d = csub(reg[m], hi);
+                const cx<float> w = cmul<false>(wt, twN[G * m]);   // W_N^(t + G m); the second factor is the same for the whole CTA
+                reg[m] = cmul<INV>(d, w);
+            }
+        }
+        __syncthreads();   // the previous transform is done with the exchange buffer
+        {   // pull this cluster's next transform into L2 (each CTA the half it reads first)
+            const long fn = f + n_pairs;
+            if (fn < batch) {
+                const char *nx = reinterpret_cast<const char *>(in + fn * N + r * M);
+#pragma unroll
+                for (int k = 0; k < (int)(M * sizeof(cx<float>) / 128 / G); ++k) prefetch_l2(nx + ((long)t + (long)G * k) * 128);
+            }
+        }
+        const cx<float> *twp = tw;
+        asm volatile("" : "+l"(twp)::"memory");
+        group_fft<float, M, E, INV, 1>(reg, t, exch, twp);
+        // ---- swap halves: rank 0 ships m >= 16, rank 1 ships m < 16; the peer must have emptied its receive buffer first
+        if (!first) cluster_wait();
+        first = false;
+#pragma unroll
+        for (int m = 0; m < HE; ++m) {
+            cx<float> v = (r == 0) ? reg[HE + m] : reg[m];
+            v.x *= scale; v.y *= scale;
+            st_cluster(peer_recv + (unsigned)(m * G * sizeof(cx<float>)), v);
+        }
+        cluster_arrive();
+        cluster_wait();
+        // ---- X[2k], X[2k+1] as one 16-byte store: k = t + G*(m + 16 r)
+        {
+            float4 *dst = reinterpret_cast<float4 *>(out + f * N) + t + (long)G * HE * r;
+#pragma unroll
+            for (int m = 0; m < HE; ++m) {
+                cx<float> own = (r == 0) ? reg[m] : reg[HE + m];
+                own.x *= scale; own.y *= scale;
+                const cx<float> oth = recv[m * G + t];
+                dst[G * m] = (r == 0) ? make_float4(own.x, own.y, oth.x, oth.y) : make_float4(oth.x, oth.y, own.x, own.y);
+            }
+        }
+        cluster_arrive();     // "my receive buffer is free again": matched by the peer's wait before its next remote stores
+        asm volatile("" ::: "memory");
+    }
+    if (!first) cluster_wait();   // nobody leaves while the peer may still write into its shared memory
+}
+#endif
+
 // ---- four-step for N = N1 * N2 (both handled by one thread group each) -----------------------------------
 // Step A: for CT adjacent columns n2, DFT over n1 (stride N2), multiply by W_N^(n2*k1), write row-major [k1][n2].
 // Global accesses are CT*sizeof(cx) contiguous bytes per row; all loads of a tile are issued before the first
