@@ -67,7 +67,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src, _, r in results:
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n" + r.stderr[-4000:])
-    r = subprocess.run([_nvcc(), "-shared", "-o", LIB] + [o for _, o, _ in results], capture_output=True, text=True)
+    # the arch flag at link time too: without it nvcc adds an empty default-arch (sm_52) device-link stub to the fat binary
+    r = subprocess.run([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + [o for _, o, _ in results],
+                       capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stderr[-4000:])
     if verbose:

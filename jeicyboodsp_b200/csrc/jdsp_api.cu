@@ -142,7 +142,10 @@ static int launch_c2c_split2(jdsp_ctx *c, const cx<float> *in, cx<float> *out, l
 }
 
 #ifndef JDSP_EMUL
-// N = 32768 on 2-CTA clusters (JDSP_FFT_NO_CLUSTER=1 falls back to the L2-paired split kernel)
+// N = 32768 on 2-CTA clusters, opt-in (JDSP_FFT_CLUSTER=1).  Measured on B200 (profiles/round2): 0.42 of the HBM peak against 0.46
+// for the L2-paired split kernel.  The 16-byte pair stores halve the load/store-unit stall (lg_throttle 6.4 -> 3.2 per issue), but
+// the two cluster barriers per transform (membar stall 2.5 per issue) and the remote stores (mio_throttle 2.3) cost more than that
+// saves in a kernel whose single CTA per SM runs load, transform, exchange and store strictly one after the other.
 template <int M, bool INV>
 static int launch_c2c_cluster2(jdsp_ctx *c, const cx<float> *in, cx<float> *out, long batch) {
     using Geo = FftCluster2Geom<M>;
@@ -255,7 +258,7 @@ static int fft_dispatch(jdsp_ctx *c, const cx<T> *in, cx<T> *out, int n, long ba
             return launch_c2c_fourstep<T, 64, 256, INV>(c, in, out, batch, tkind);
         case 32768:
 #ifndef JDSP_EMUL
-            if constexpr (sizeof(T) == 4) { if (!getenv("JDSP_FFT_NO_CLUSTER") && !getenv("JDSP_FFT_NO_SPLIT") && !getenv("JDSP_FFT_FUSED")) return launch_c2c_cluster2<16384, INV>(c, (const cx<float> *)in, (cx<float> *)out, batch); }
+            if constexpr (sizeof(T) == 4) { if (getenv("JDSP_FFT_CLUSTER") && !getenv("JDSP_FFT_NO_SPLIT") && !getenv("JDSP_FFT_FUSED")) return launch_c2c_cluster2<16384, INV>(c, (const cx<float> *)in, (cx<float> *)out, batch); }
 #endif
             if constexpr (sizeof(T) == 4) { if (!getenv("JDSP_FFT_NO_SPLIT") && !getenv("JDSP_FFT_FUSED")) return launch_c2c_split2<16384, INV>(c, (const cx<float> *)in, (cx<float> *)out, batch); }
             if constexpr (sizeof(T) == 4) { if (getenv("JDSP_FFT_FUSED")) return launch_c2c_fused<128, 256, INV>(c, in, out, batch); }

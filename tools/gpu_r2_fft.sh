@@ -6,9 +6,9 @@ timeout 600 python -m pytest tests -x -q -m gpu -k "fft" > gpurun_out/pytest_$TA
 tail -3 gpurun_out/pytest_$TAG.txt
 timeout 300 python tools/sweep_quick.py 28 13 > gpurun_out/sweep_$TAG.log 2>&1; RC=$?
 cat gpurun_out/sweep_$TAG.log
-JDSP_FFT_NO_CLUSTER=1 timeout 300 python tools/sweep_quick.py 28 15 > gpurun_out/sweep_${TAG}_nocluster.log 2>&1
-cat gpurun_out/sweep_${TAG}_nocluster.log
+JDSP_FFT_CLUSTER=1 timeout 300 python tools/sweep_quick.py 28 15 > gpurun_out/sweep_${TAG}_cluster.log 2>&1
+cat gpurun_out/sweep_${TAG}_cluster.log
 if [ $RC -eq 0 ]; then
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:cluster2 -s 1 -c 1 -o gpurun_out/ncu_$TAG python tools/sweep_quick.py 26 15 > gpurun_out/ncu_$TAG.log 2>&1
+  JDSP_FFT_CLUSTER=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:cluster2 -s 1 -c 1 -o gpurun_out/ncu_$TAG python tools/sweep_quick.py 26 15 > gpurun_out/ncu_$TAG.log 2>&1
   tail -2 gpurun_out/ncu_$TAG.log
 fi
