@@ -218,11 +218,10 @@ struct jdsp_mfcc_plan {
     jdsp_mfcc_params p;
     std::vector<double> weight;  // rgdFilterBank
     std::vector<int32_t> chan;   // rgdFiBins
-    // device tables of mfcc_kernel (kernels_mfcc.cuh): window, DCT x lifter, and the filterbank laid out per thread slot
-    float *d_win_half = nullptr, *d_dct = nullptr, *d_slot_w = nullptr;
-    uint32_t *d_slot_ctl = nullptr, *d_refs = nullptr;
-    int *d_slot_pid = nullptr;
-    int n_pieces = 0, lmax = 0, cpt = 0;
+    // device tables of mfcc_kernel (kernels_mfcc.cuh): window, DCT x lifter, and the filterbank cut into per-warp pieces
+    float *d_win_half = nullptr, *d_dct = nullptr, *d_tri = nullptr;
+    int *d_chan_tab = nullptr, *d_grp_len = nullptr;
+    int n_tri = 0;
 };
 
 extern "C" {
@@ -245,8 +244,7 @@ int jdsp_mfcc_plan_destroy(jdsp_ctx *c, jdsp_mfcc_plan *pl) {
     if (!pl) return JDSP_OK;
     REQUIRE(c, "ctx is null");
     cudaStreamSynchronize(c->stream);
-    cudaFree(pl->d_win_half); cudaFree(pl->d_dct); cudaFree(pl->d_slot_w); cudaFree(pl->d_slot_ctl); cudaFree(pl->d_slot_pid);
-    cudaFree(pl->d_refs);
+    cudaFree(pl->d_win_half); cudaFree(pl->d_dct); cudaFree(pl->d_tri); cudaFree(pl->d_chan_tab); cudaFree(pl->d_grp_len);
     delete pl;
     return JDSP_OK;
 }
@@ -277,50 +275,35 @@ int jdsp_mfcc_plan_create(jdsp_ctx *c, const jdsp_mfcc_params *p, jdsp_mfcc_plan
         if (w < 0) w = 0;
         pl->weight[i] = w;
     }
-    // The kernel's view of the filterbank.  Thread t of a frame group (G = nbin/16 threads) holds the contiguous bins
-    // 8t..8t+7 (low chain, ascending; the last thread also bin nbin/2) and nbin-8t..nbin-8t-7 (high chain, descending; "bin
-    // nbin" of thread 0 does not exist).  A piece = a maximal run of bins of one thread range with the same channel index;
-    // pieces are numbered in bin order, so the pieces of one index are consecutive and run_start[c] finds them.
-    const int G = nbin / 16, KP = 8, NSLOT = 2 * KP + 1;
-    std::vector<int> range(nbin), piece(nbin);
-    for (int i = 0; i < nbin; ++i) range[i] = i <= nbin / 2 ? (i == nbin / 2 ? G - 1 : i / KP) : G + (nbin - i) / KP;
-    for (int i = 0, id = -1; i < nbin; ++i) {
-        if (i == 0 || range[i] != range[i - 1] || pl->chan[i] != pl->chan[i - 1]) ++id;
-        piece[i] = id;
-    }
-    pl->n_pieces = piece[nbin - 1] + 1;
-    std::vector<float> slot_w((size_t)NSLOT * G, 0.f);
-    std::vector<uint32_t> slot_ctl((size_t)G, 0u);
-    std::vector<int> slot_pid((size_t)2 * G, 0), run_start((size_t)C + 3, pl->n_pieces);
-    for (int t = 0; t < G; ++t) {
-        for (int j = 0; j < KP; ++j) {
-            const int lo = KP * t + j, hi = nbin - KP * t - j;
-            slot_w[(size_t)j * G + t] = (float)pl->weight[lo];
-            if (j > 0 && piece[lo] != piece[lo - 1]) slot_ctl[t] |= 1u << j;
-            if (hi < nbin) {
-                slot_w[(size_t)(KP + 1 + j) * G + t] = (float)pl->weight[hi];
-                if (j > 0 && hi + 1 < nbin && piece[hi] != piece[hi + 1]) slot_ctl[t] |= 1u << (16 + j);
+    // The kernel's view of the filterbank.  The channel index steps by at most one per bin, so the bins of index v form one run
+    // [first[v], first[v+1]).  Channel c (MelFilterBank, :157-168) = the (1-w) shares of the bins of index c plus the w shares of the
+    // bins of index c+1: one contiguous support with a triangular weight list.  A warp handles four adjacent channels at once, so
+    // their lists are padded (zero weights) to one length; a support that would run past the last bin is shifted down instead.
+    std::vector<int> first((size_t)C + 3, nbin);
+    for (int i = nbin - 1; i >= 0; --i) first[pl->chan[i]] = i;
+    for (int v = C + 1; v >= 0; --v) if (first[v] > first[v + 1]) first[v] = first[v + 1];
+    const int cpad = (C + 3) & ~3;
+    std::vector<int> chan_tab((size_t)2 * cpad, 0), grp_len((size_t)cpad / 4, 0);
+    std::vector<float> tri;
+    for (int c0 = 0; c0 < cpad; c0 += 4) {
+        int n = 0;
+        for (int c = c0; c < c0 + 4 && c < C; ++c) n = std::max(n, first[c + 2] - first[c]);
+        grp_len[c0 / 4] = n;
+        for (int c = c0; c < c0 + 4; ++c) {
+            int start = c < C ? first[c] : 0;
+            if (start + n > nbin) start = nbin - n;
+            chan_tab[2 * c] = start;
+            chan_tab[2 * c + 1] = (int)tri.size();
+            for (int k = 0; k < n; ++k) {
+                const int i = start + k;
+                float wgt = 0.f;
+                if (c < C && pl->chan[i] == c) wgt = (float)(1.0 - pl->weight[i]);
+                else if (c < C && pl->chan[i] == c + 1) wgt = (float)pl->weight[i];
+                tri.push_back(wgt);
             }
         }
-        slot_pid[t] = piece[KP * t];
-        slot_pid[G + t] = piece[nbin - KP * t < nbin ? nbin - KP * t : nbin - 1];
     }
-    slot_w[(size_t)KP * G + (G - 1)] = (float)pl->weight[nbin / 2];
-    if (piece[nbin / 2] != piece[nbin / 2 - 1]) slot_ctl[G - 1] |= 1u << KP;
-    for (int i = nbin - 1; i >= 0; --i) run_start[pl->chan[i]] = piece[i];   // first piece of every index that occurs ...
-    for (int v = C + 1; v >= 0; --v) if (run_start[v] > run_start[v + 1]) run_start[v] = run_start[v + 1];   // ... the next one's otherwise
-    // channel c (MelFilterBank, :157-168) = the (1-w) shares of the bins of index c plus the w shares of the bins of index c+1: a
-    // fixed-length list per channel, padded with the always-zero piece n_pieces; thread t of a frame group sums channels t + G*i
-    pl->lmax = 1;
-    for (int v = 0; v <= C; ++v) pl->lmax = std::max(pl->lmax, run_start[v + 1] - run_start[v]);
-    pl->cpt = (C + G - 1) / G;
-    std::vector<uint32_t> refs((size_t)pl->cpt * pl->lmax * G, (uint32_t)pl->n_pieces * 0x10001u);
-    for (int ch = 0; ch < C; ++ch)
-        for (int l = 0; l < pl->lmax; ++l) {
-            const uint32_t u = run_start[ch] + l < run_start[ch + 1] ? run_start[ch] + l : pl->n_pieces;
-            const uint32_t v = run_start[ch + 1] + l < run_start[ch + 2] ? run_start[ch + 1] + l : pl->n_pieces;
-            refs[((size_t)(ch / G) * pl->lmax + l) * G + ch % G] = u | (v << 16);
-        }
+    pl->n_tri = (int)tri.size();
     // M4 DCT (:176-183) times M5 lifter (:185-192)
     std::vector<float> dct((size_t)C * 16, 0.f);   // [channel][cepstrum], rows padded to 16
     for (int i = 1; i <= p->n_cep; ++i) {
@@ -331,10 +314,9 @@ int jdsp_mfcc_plan_create(jdsp_ctx *c, const jdsp_mfcc_params *p, jdsp_mfcc_plan
     for (int i = 0; i < W; ++i) wh[i] = (float)(0.5 * (p->win_a0 - p->win_a1 * cos(2 * p->pi_literal * i / (W - 1))));
     int rc = upload(c, wh, &pl->d_win_half);
     if (rc == JDSP_OK) rc = upload(c, dct, &pl->d_dct);
-    if (rc == JDSP_OK) rc = upload(c, slot_w, &pl->d_slot_w);
-    if (rc == JDSP_OK) rc = upload(c, slot_ctl, &pl->d_slot_ctl);
-    if (rc == JDSP_OK) rc = upload(c, slot_pid, &pl->d_slot_pid);
-    if (rc == JDSP_OK) rc = upload(c, refs, &pl->d_refs);
+    if (rc == JDSP_OK) rc = upload(c, tri, &pl->d_tri);
+    if (rc == JDSP_OK) rc = upload(c, chan_tab, &pl->d_chan_tab);
+    if (rc == JDSP_OK) rc = upload(c, grp_len, &pl->d_grp_len);
     if (rc != JDSP_OK) { jdsp_mfcc_plan_destroy(c, pl); return rc; }
     *out = pl;
     return JDSP_OK;
@@ -350,16 +332,16 @@ int jdsp_mfcc_plan_tables(jdsp_mfcc_plan *pl, double *weight, int32_t *chan) {
 template <int NC, int MU> static int launch_mfcc(jdsp_ctx *c, const MfccArgs &a) {
     using Geo = MfccGeom<NC>;
     auto kfn = mfcc_kernel<NC, MU>;
-    const size_t smem = Geo::smem(a.n_mel, a.n_pieces, a.lmax, a.cpt, a.xspan);
+    const size_t smem = Geo::smem(a.n_mel, a.n_tri, a.slot);
     if (smem > 227 * 1024) return fail(JDSP_ERR_UNSUPPORTED, "MFCC: frame hop / channel count too large for the kernel's shared-memory layout");
     TRY(opt_in_smem(kfn, smem));
-    int per_sm = 4;
+    int per_sm = 2;
 #ifndef JDSP_EMUL
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, Geo::NT, smem));
     if (per_sm < 1) return fail(JDSP_ERR_CUDA, "MFCC kernel does not fit an SM");
 #endif
     const long batches = a.n_utts * ((a.n_frames + Geo::FB - 1) / Geo::FB);
-    JDSP_LAUNCH_PTR(kfn, dim3(grid_for(c, (batches + Geo::NW - 1) / Geo::NW, per_sm)), dim3(Geo::NT), smem, c->stream, a);
+    JDSP_LAUNCH_PTR(kfn, dim3(grid_for(c, batches, per_sm)), dim3(Geo::NT), smem, c->stream, a);
     return launch_check(c);
 }
 
@@ -382,11 +364,12 @@ int jdsp_mfcc_frames_i16_dev(jdsp_ctx *c, jdsp_mfcc_plan *pl, const int16_t *d_i
     MfccArgs a;
     a.in = d_in; a.in_pitch = in_pitch; a.n_utts = n_utts; a.n_frames = nf;
     a.feat = d_feat; a.feat_pitch = feat_pitch; a.win_half = pl->d_win_half; a.tw = (const cf *)tw; a.twr = (const float2 *)twr;
-    a.slot_w = pl->d_slot_w; a.slot_ctl = pl->d_slot_ctl; a.slot_pid = pl->d_slot_pid; a.refs = pl->d_refs; a.dct = pl->d_dct;
+    a.tri = pl->d_tri; a.chan_tab = (const int2 *)pl->d_chan_tab; a.grp_len = pl->d_grp_len; a.dct = pl->d_dct;
     a.frame_len = p.frame_len; a.hop = p.hop; a.n_mel = p.n_mel; a.n_cep = p.n_cep; a.preemph = (float)p.preemph;
-    a.n_pieces = pl->n_pieces; a.lmax = pl->lmax; a.cpt = pl->cpt;
-    // samples per PCM staging buffer: 8 in front (16-byte aligned span start), the frames of a step, n_fft behind the last frame start
-    a.xspan = 8 + (NC == 256 ? p.hop : 0) + p.n_fft + 24;
+    a.n_tri = pl->n_tri;
+    // consecutive frames of a batch start `slot` samples apart in the staging buffer: overlapping (or nearly adjacent) frames arrive as
+    // one copy of the whole span, frames further apart one by one
+    a.slot = p.hop <= p.frame_len + 8 ? p.hop : p.frame_len + 8;
     // packed points t + G*m, m >= MU, lie past frame_len for every thread: the 13-row instance covers frames of up to 13*n_fft/32
     // samples (the bench preset's 400 of 512)
     if (NC == 256) return p.frame_len <= 13 * 32 ? launch_mfcc<256, 13>(c, a) : launch_mfcc<256, 16>(c, a);

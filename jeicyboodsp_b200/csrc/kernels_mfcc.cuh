@@ -1,19 +1,24 @@
 // kernels_mfcc.cuh -- mfcc_kernel: M2-M5, MFCCFeatureExtraction / MelFilterBank / DCT / Liftering
-// (MFCCFeatureExtraction_auto_version1.cpp:154-231) with generalised framing, one thread GROUP per frame.
+// (MFCCFeatureExtraction_auto_version1.cpp:154-231) with generalised framing.
 //
-// A warp owns a BATCH of 32 consecutive frames of one utterance and never meets the other warps of its CTA.
-// Phase A, per step of 32/G frames (G = NC/16 threads per frame: a half warp at n_fft 512, a warp at n_fft 1024):
-//   * the step's PCM span arrives by one per-warp TMA bulk copy, two steps ahead (one mbarrier per staging buffer);
+// A CTA (8 warps) owns a BATCH of 32 consecutive frames of one utterance; the batch's PCM arrives by TMA bulk copy (one copy of
+// the whole span when frames overlap, one per frame otherwise) while the previous batch is in Phase B.
+// Phase A, one thread GROUP per frame (G = NC/16 threads: a half warp at n_fft 512, a warp at n_fft 1024), no CTA barrier:
 //   * pre-emphasis (:208-210), window (:212-214) and the packed real transform run on 16 points per thread;
-//   * the mirrored bins NC-k come from the partner thread by shuffles, the real spectrum is untangled in registers and only
-//     |X| (:218-220) goes through shared memory, once, so that every thread then holds 8 + 8 (+1) CONTIGUOUS bins;
-//   * the two-tap filterbank of MelFilterBank (:154-174) is a pair of running sums (sum |X|, sum w |X|) per thread, flushed as a
-//     "piece" wherever the bin's channel index (rgdFiBins) changes; pieces are numbered in bin order, a host-built table lists
-//     the (at most LMAX) pieces of every channel, so a channel sum is a fixed-order, fixed-length sum: no atomics, no
-//     data-dependent loops, bit-reproducible.
-// Phase B, once per batch, one LANE per frame: ln (:170-172) and the DCT (:176-183) with the lifter (:185-192) folded into the
-// table, whose rows every lane reads at the same address (broadcast); the 32 feature rows leave as one contiguous run.
-// No CTA barrier after the prologue.
+//   * the mirrored bins NC-k come from the partner thread by shuffles, the real spectrum is untangled in registers and |X|
+//     (:218-220) is written once into the batch's magnitude matrix mag[bin][frame] (row pitch 36 words).
+// Phase B (nothing in it is data dependent, every table read is a broadcast):
+//   B1  MelFilterBank (:154-174) + ln (:170-172): a thread owns (channel, four frames) and walks the channel's support -- the bins of
+//       index c with weight 1-w, then the bins of index c+1 with weight w (one host-built triangular weight list per channel, the four
+//       channels of a warp padded to one length) -- reading four frames of a bin as one 16-byte word: no flush logic, no atomics;
+//   B2  DCT (:176-183) with the lifter (:185-192) folded into the table: one lane per frame, four cepstra per warp, stored straight
+//       into the feature rows.
+// Two CTA barriers per 32 frames.  (The round-1/early round-2 kernels did the filterbank per frame inside the frame's thread
+// group: contiguous-bin relayout, running sums flushed at run-time channel boundaries and a per-channel gather cost ~200 of
+// their 563 warp instructions per frame, more than the transform itself; a first batched version with per-warp bin ranges,
+// pieces and four barriers spent as long at the barriers as it saved; balancing B1 and B2 over all eight warps -- wide channels
+// cut into segments, cepstra split over channel halves -- halved the barrier stalls but cost 5 % more instructions and was 4 %
+// slower, 24.1 against 23.0 ms: the second resident CTA already fills the barrier gaps.)
 #pragma once
 #include "kernels_stft.cuh"
 
@@ -25,42 +30,40 @@ struct MfccArgs {
     const float *win_half;                 // [frame_len] 0.5 * w
     const cf *tw;                          // per-pass Stockham twiddles for length NC (TwLayout)
     const float2 *twr;                     // [NC/2+1] (cos, sin)(2*pi*k/N)
-    const float *slot_w;                   // [17][G] filterbank weight (rgdFilterBank) of the bin in slot j of thread t
-    const uint32_t *slot_ctl;              // [G] bit j (1..8): low-chain slot j opens a new piece; bit 16+j (1..7): high chain
-    const int *slot_pid;                   // [2][G] piece id of the first low-chain / high-chain piece
-    const uint32_t *refs;                  // [cpt][lmax][G] pieces of channel t + G*i: low half (1-w) share, high half w share
+    const float *tri;                      // [n_tri] triangular weights of every channel over its support, channel after channel
+    const int2 *chan_tab;                  // [round_up(n_mel, 4)] (first bin, offset into tri); the four channels of a warp share one length
+    const int *grp_len;                    // [round_up(n_mel, 4) / 4] that length
     const float *dct;                      // [n_mel][16] sqrt(2/C)*cos(...) * lifter, zero past n_cep
-    int frame_len, hop, n_mel, n_cep, n_pieces, lmax, cpt, xspan;
+    int frame_len, hop, n_mel, n_cep, n_tri;
+    int slot;                              // samples between the staged starts of consecutive frames: hop (one span copy) or frame_len + 8
     float preemph;
 };
 
 template <int NC>
 struct MfccGeom {
-    static constexpr int N = 2 * NC, E = 16, G = NC / E, NT = 128, NW = NT / 32, FPW = 32 / G, NGRP = NT / G, FB = 32;
-    static constexpr int KP = NC / 2 / G;                 // bin pairs (k, NC-k) per thread
-    static constexpr int NSLOT = 2 * KP + 1;              // + bin NC/2 (last thread)
+    static constexpr int N = 2 * NC, E = 16, G = NC / E, NT = 256, NW = NT / 32, FPW = 32 / G, NGRP = NT / G, FB = 32;
+    static constexpr int STEPS = FB / NGRP;               // steps of NGRP frames per batch
+    static constexpr int MP = 36;                         // row pitch of mag[bin][frame] and logmel[channel][frame]: 16-byte rows
     static constexpr int PADN = padded_len(NC);
-    static constexpr int GBUF = PADN + 9;                 // exchange buffer of a frame group; doubles as its |X| buffer (floats, the
-                                                          // second group of a warp 16 banks further) and, per warp, as the batch's output rows
+    static constexpr int GBUF = PADN;                     // exchange buffer of a frame group
     static constexpr int NTW = TwLayout<NC, E>::total;
-    static constexpr int MAXMEL = 64, MAXCEP = 16;
+    static constexpr int MAXMEL = 64, MAXCEP = 16, CPW = 4;   // cepstra per warp in B2
     static constexpr size_t OFF_FBUF = 0;
-    static constexpr size_t OFF_TW = OFF_FBUF + (size_t)NGRP * GBUF * sizeof(cf);
+    static constexpr size_t OFF_MAG = OFF_FBUF + (size_t)NGRP * GBUF * sizeof(cf);           // [NC+1][MP] (row NC: the unused "bin NC")
+    static constexpr size_t OFF_TW = OFF_MAG + (size_t)(NC + 1) * MP * sizeof(float);
     static constexpr size_t OFF_WIN = (OFF_TW + (size_t)NTW * sizeof(cf) + 15) & ~(size_t)15;
-    static constexpr size_t OFF_SLOTW = OFF_WIN + (size_t)N * sizeof(float);                 // [NSLOT][G]
-    static constexpr size_t OFF_BAR = (OFF_SLOTW + (size_t)NSLOT * G * sizeof(float) + 15) & ~(size_t)15;
-    static constexpr size_t OFF_VAR = OFF_BAR + (size_t)NW * 2 * sizeof(uint64_t);           // run-time sized regions follow
-    // run-time sized: dct [n_mel][16], refs [cpt][lmax][G], pieces [NGRP][n_pieces+1] float2, mel sums [NW][FB][n_mel|1], PCM [NW][2][xspan]
-    static size_t smem(int n_mel, int n_pieces, int lmax, int cpt, int xspan) {
-        size_t s = OFF_VAR + (size_t)n_mel * 16 * 4 + (size_t)cpt * lmax * G * 4;
-        s = (s + 7) & ~(size_t)7;
-        s += (size_t)NGRP * (n_pieces + 1) * 8 + (size_t)NW * FB * (n_mel | 1) * 4;
+    static constexpr size_t OFF_BAR = OFF_WIN + (size_t)N * sizeof(float);
+    static constexpr size_t OFF_VAR = OFF_BAR + 16;                                          // run-time sized regions follow
+    // run-time sized: logmel [n_mel][MP], dct [n_mel][16], chan_tab [cpad] int2, grp_len [cpad/4], tri [n_tri], PCM [(FB-1)*slot + N]
+    static size_t smem(int n_mel, int n_tri, int slot) {
+        const int cpad = (n_mel + 3) & ~3;
+        size_t s = OFF_VAR + (size_t)n_mel * MP * 4 + (size_t)n_mel * 16 * 4 + (size_t)cpad * 8 + (size_t)(cpad / 4) * 4 + (size_t)n_tri * 4;
         s = (s + 15) & ~(size_t)15;
-        return s + (size_t)NW * 2 * xspan * 2;
+        return s + ((size_t)(FB - 1) * slot + N) * 2;
     }
     static_assert(G == 16 || G == 32, "a frame group is a half warp or a warp");
-    static_assert(KP == 8, "eight bin pairs per thread");
-    static_assert(NGRP * GBUF * sizeof(cf) / NW >= FB * MAXCEP * sizeof(float), "a warp's exchange buffers hold the batch's output rows");
+    static_assert(NC / 2 / G == 8, "eight bin pairs per thread");
+    static_assert(OFF_MAG % 16 == 0 && OFF_TW % 16 == 0, "16-byte rows");
 };
 
 JDSP_DEV float log_fast(float x) {
@@ -72,213 +75,176 @@ JDSP_DEV float log_fast(float x) {
 }
 // MU: packed points t + G*m with m >= MU lie past frame_len for every thread (the frame is zero-padded to n_fft there)
 template <int NC, int MU>
-__global__ void __launch_bounds__(MfccGeom<NC>::NT, 4) mfcc_kernel(MfccArgs a) {
+__global__ void __launch_bounds__(MfccGeom<NC>::NT, 2) mfcc_kernel(MfccArgs a) {
     using Geo = MfccGeom<NC>;
-    constexpr int E = Geo::E, G = Geo::G, NT = Geo::NT, NW = Geo::NW, FPW = Geo::FPW, KP = Geo::KP, NSLOT = Geo::NSLOT, FB = Geo::FB;
-    constexpr int GBUF = Geo::GBUF, HM = E / 2;
-    constexpr int MSTRIDE = G + G / 16;
+    constexpr int E = Geo::E, G = Geo::G, NT = Geo::NT, NW = Geo::NW, FPW = Geo::FPW, NGRP = Geo::NGRP, FB = Geo::FB;
+    constexpr int GBUF = Geo::GBUF, HM = E / 2, MP = Geo::MP, CPW = Geo::CPW;
     JDSP_DYN_SMEM(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane / G, t = lane % G, gi = tid / G;
-    const int W = a.frame_len, hop = a.hop, C = a.n_mel, NCEP = a.n_cep, NP1 = a.n_pieces + 1, LMAX = a.lmax, CPT = a.cpt, XSPAN = a.xspan;
-    const int MPITCH = C | 1;
+    const int W = a.frame_len, hop = a.hop, C = a.n_mel, CPAD = (C + 3) & ~3, NCEP = a.n_cep, NTRI = a.n_tri, SLOT = a.slot;
     const float npre = -a.preemph;
     const long n_frames = a.n_frames, in_pitch = a.in_pitch, feat_pitch = a.feat_pitch;
 
     cf *fbuf = reinterpret_cast<cf *>(smem_raw + Geo::OFF_FBUF);
+    float *mag = reinterpret_cast<float *>(smem_raw + Geo::OFF_MAG);
     cf *tw = reinterpret_cast<cf *>(smem_raw + Geo::OFF_TW);
     float *winh = reinterpret_cast<float *>(smem_raw + Geo::OFF_WIN);
-    float *slotw = reinterpret_cast<float *>(smem_raw + Geo::OFF_SLOTW);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + Geo::OFF_BAR);
-    float *dct = reinterpret_cast<float *>(smem_raw + Geo::OFF_VAR);
-    uint32_t *refs = reinterpret_cast<uint32_t *>(dct + C * 16);
-    size_t off = (Geo::OFF_VAR + (size_t)C * 16 * 4 + (size_t)CPT * LMAX * G * 4 + 7) & ~(size_t)7;
-    float2 *pieces = reinterpret_cast<float2 *>(smem_raw + off);
-    off += (size_t)Geo::NGRP * NP1 * 8;
-    float *melb = reinterpret_cast<float *>(smem_raw + off) + warp * FB * MPITCH;
-    off = (off + (size_t)NW * FB * MPITCH * 4 + 15) & ~(size_t)15;
-    int16_t *xs_w = reinterpret_cast<int16_t *>(smem_raw + off) + (size_t)warp * 2 * XSPAN;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + Geo::OFF_BAR);
+    float *logmel = reinterpret_cast<float *>(smem_raw + Geo::OFF_VAR);
+    float *dct = logmel + C * MP;
+    int2 *chtab = reinterpret_cast<int2 *>(dct + C * 16);
+    int *glen = reinterpret_cast<int *>(chtab + CPAD);
+    float *tri = reinterpret_cast<float *>(glen + CPAD / 4);
+    const size_t off_pcm = (Geo::OFF_VAR + (size_t)C * MP * 4 + (size_t)C * 16 * 4 + (size_t)CPAD * 8 + (size_t)(CPAD / 4) * 4 + (size_t)NTRI * 4 + 15) & ~(size_t)15;
+    int16_t *xs = reinterpret_cast<int16_t *>(smem_raw + off_pcm);
 
     // ---- tables (once per CTA) -----------------------------------------------------------------------------------
     for (int i = tid; i < Geo::NTW; i += NT) tw[i] = a.tw[i];
     for (int i = tid; i < 2 * NC; i += NT) winh[i] = i < W ? a.win_half[i] : 0.f;
-    for (int i = tid; i < NSLOT * G; i += NT) slotw[i] = a.slot_w[i];
     for (int i = tid; i < C * 16; i += NT) dct[i] = a.dct[i];
-    for (int i = tid; i < CPT * LMAX * G; i += NT) refs[i] = a.refs[i];
-    for (int i = tid; i < Geo::NGRP; i += NT) pieces[i * NP1 + NP1 - 1] = make_float2(0.f, 0.f);   // the piece that table padding points at
-    uint64_t *bar = bars + warp * 2;
-    if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
+    for (int i = tid; i < CPAD; i += NT) chtab[i] = a.chan_tab[i];
+    for (int i = tid; i < CPAD / 4; i += NT) glen[i] = a.grp_len[i];
+    for (int i = tid; i < NTRI; i += NT) tri[i] = a.tri[i];
+    for (int i = tid; i < (NC + 1) * MP; i += NT) mag[i] = 0.f;          // columns of frames past the end of an utterance stay finite
+    for (int i = tid; i < (FB - 1) * SLOT + 2 * NC; i += NT) xs[i] = 0;   // and those frames transform stale, finite samples
+    if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
 
     // ---- per-thread constants ------------------------------------------------------------------------------------
     cf *buf = fbuf + gi * GBUF;
-    float *mag = reinterpret_cast<float *>(buf) + 14 * g;      // |X| by bin (pad16); 16 banks between the halves of a warp
-    float *obuf = reinterpret_cast<float *>(fbuf + (size_t)warp * (32 / G) * GBUF);
-    float2 *pc = pieces + gi * NP1;
-    const uint32_t ctl = a.slot_ctl[t];
-    const int pid_lo0 = a.slot_pid[t], pid_hi0 = a.slot_pid[G + t];
-    float *mag_own = mag + pad16(t);                           // bin t + G*m at mag_own[m * MSTRIDE]
-    float *mag_mir = mag + pad16(NC - t);                      // bin NC - t - G*m at mag_mir[-m * MSTRIDE]
-    const float *lo_p = mag + KP * t + t / 2;                  // bin KP*t + j at lo_p[j]           (pad16, j < 8)
-    const int q0 = NC - KP * t;                                // mirror of the thread's first bin
-    const float *hi0_p = mag + q0 + q0 / 16;                   // bin NC - KP*t (thread 0: bin "NC", never used)
-    const float *hi_p = mag + q0 + ((t & 1) ? q0 / 16 : q0 / 16 - 1);   // bin NC - KP*t - j at hi_p[-j], 1 <= j < 8
-    const float *mid_p = mag + pad16(NC / 2);
     const float2 *win2 = reinterpret_cast<const float2 *>(winh) + t;
-    const float *sw_t = slotw + t;
     const float2 wt = a.twr[t], cs_half = a.twr[NC / 2];
     const int partner = (G - t) & (G - 1);
+    // frame fb = j*NGRP + warp*FPW + g of a batch sits in column fb of mag
+    const int col0 = warp * FPW + g;
+    float *mag_own = mag + t * MP + col0;                      // bin t + G*m at mag_own[m * G * MP]
+    float *mag_mir = mag + (NC - t) * MP + col0;               // bin NC - t - G*m at mag_mir[-m * G * MP]
+    float *mag_mid = mag + (NC / 2) * MP + col0;
+    const uint32_t *fw0 = reinterpret_cast<const uint32_t *>(xs + gi * SLOT) + t;
 
-    // ---- work: batches of FB consecutive frames of one utterance per warp, FPW frames per step ---------------------------
+    // ---- work: batches of FB consecutive frames of one utterance per CTA ---------------------------------------------------
     const long batches_per_utt = (n_frames + FB - 1) / FB;
     const long n_batches = a.n_utts * batches_per_utt;
-    const long stride = (long)gridDim.x * NW;
-    struct Cursor {     // (batch, step within it) of a warp's walk; the fetching cursor runs two steps ahead of the computing one
-        StridedDivmod d; long batch; int j;
-        JDSP_DEV Cursor(long b0, long st, long per) : d(b0, st, per), batch(b0), j(0) {}
-    };
-    Cursor cons((long)blockIdx.x * NW + warp, stride, batches_per_utt), prod = cons;
-    if (cons.batch >= n_batches) return;
-    auto frames_in = [&](const Cursor &c) { const long left = n_frames - c.d.r * FB; return left < FB ? (int)left : FB; };
-    auto advance = [&](Cursor &c) {
-        if ((c.j + 1) * FPW >= frames_in(c)) { c.j = 0; c.batch += stride; c.d.next(); } else ++c.j;
-    };
-    auto fetch = [&](const Cursor &c, int bufi) {    // lane 0: one bulk copy of the step's PCM span into staging buffer bufi
-        const long f0 = c.d.r * FB + (long)c.j * FPW;
-        const int nf = (n_frames - f0 < FPW) ? (int)(n_frames - f0) : FPW;
-        const unsigned bytes = (unsigned)(((nf - 1) * hop + W) * 2);
-        mbar_expect_tx(&bar[bufi], bytes);
-        bulk_g2s(xs_w + bufi * XSPAN + 8, a.in + c.d.q * in_pitch + f0 * hop, bytes, &bar[bufi]);
-    };
-    if (lane == 0) fetch(prod, 0);
-    advance(prod);
-    if (lane == 0 && prod.batch < n_batches) fetch(prod, 1);
-    unsigned phase0 = 0, phase1 = 0;
-    int cur = 0;
-
-    while (cons.batch < n_batches) {
-        const int nfb = frames_in(cons);
-        const int slot = cons.j * FPW + g;                     // this group's frame within the batch
-        if (cur == 0) { mbar_wait(&bar[0], phase0); phase0 ^= 1u; } else { mbar_wait(&bar[1], phase1); phase1 ^= 1u; }
-        // ---- pre-emphasis (:208-210), window (:212-214): packed point n = t + G*m holds samples 2n, 2n+1 --------------
-        cf reg[E];
-        {
-            const uint32_t *fw = reinterpret_cast<const uint32_t *>(xs_w + cur * XSPAN + 8 + g * hop) + t;
-            float carry = 0.f;     // thread 0: the odd sample of the last thread's previous point
-#pragma unroll
-            for (int m = 0; m < E; ++m) {
-                if (m < MU) {
-                    const float2 x = s16x2_to_f32(fw[G * m]);
-                    const float up = __shfl_sync(0xffffffffu, x.y, (t + G - 1) & (G - 1), G);   // sample 2n-1 lives one thread down
-                    const float xm = (t == 0) ? carry : up;
-                    carry = up;
-                    const float2 w = win2[G * m];
-                    float2 v = __fmul2_rn(__ffma2_rn(make_float2(xm, x.x), make_float2(npre, npre), x), w);
-                    if (m == 0 && t == 0) v.x = 0.f;   // element 0 is never pre-emphasised: stays 0
-                    reg[m] = c2(v);
-                } else {
-                    reg[m] = cmake<float>(0.f, 0.f);
-                }
+    auto frames_in = [&](long r) { const long left = n_frames - r * FB; return left < FB ? (int)left : FB; };
+    // warp 0 stages a batch: one bulk copy of the whole span when consecutive frames are `hop` apart in the buffer, else one per frame
+    auto fetch = [&](long q, long r) {
+        const int nf = frames_in(r);
+        const int16_t *src = a.in + q * in_pitch + r * FB * hop;
+        if (SLOT == hop) {
+            if (lane == 0) {
+                const unsigned bytes = (unsigned)(((nf - 1) * hop + W) * 2);
+                mbar_expect_tx(bar, bytes);
+                bulk_g2s(xs, src, bytes, bar);
             }
-        }
-        __syncwarp();
-        // this staging buffer is free again: fetch the step two ahead into it
-        advance(prod);
-        if (lane == 0 && prod.batch < n_batches) fetch(prod, cur);
-        // ---- packed real transform ------------------------------------------------------------------------------
-        group_fft<float, NC, E, false, 0>(reg, t, buf, tw);
-        group_sync<0>();       // the last pass has been read out of the exchange buffer: it now takes the magnitudes
-        // ---- |X| (:218-220) of the thread's bin pairs (k, NC-k), k = t + G*m; the mirrored bin lives in the partner thread -----
-        const float2 wtb = opaque(wt);
-#pragma unroll
-        for (int m = 0; m < HM; ++m) {
-            cf Bm;
-            Bm.x = __shfl_sync(0xffffffffu, reg[E - 1 - m].x, partner, G);
-            Bm.y = __shfl_sync(0xffffffffu, reg[E - 1 - m].y, partner, G);
-            if (t == 0) Bm = (m == 0) ? reg[0] : reg[E - m];     // thread 0 pairs with itself: bin NC - G*m is its own point E - m
-            const float2 cs = post_twiddle(wtb, m);
-            cf X1, X2;
-            untangle2x(reg[m], Bm, cs.x, cs.y, X1, X2);
-            mag_own[m * MSTRIDE] = sqrt_fast(X1.x * X1.x + X1.y * X1.y);
-            mag_mir[-m * MSTRIDE] = sqrt_fast(X2.x * X2.x + X2.y * X2.y);   // thread 0, m = 0: slot of the unused "bin NC"
-        }
-        if (t == 0) {
-            cf X1, X2;
-            untangle2x(reg[HM], reg[HM], cs_half.x, cs_half.y, X1, X2);      // bin NC/2 (thread 0's point HM) pairs with itself
-            *const_cast<float *>(mid_p) = sqrt_fast(X1.x * X1.x + X1.y * X1.y);
-        }
-        group_sync<0>();
-        // ---- M3 MelFilterBank (:154-174) on contiguous bins: low chain KP*t + j ascending (then bin NC/2, which belongs to the
-        // last thread), high chain NC - KP*t - j descending; a piece = (sum |X|, sum w |X|) of a run of one channel index
-        {
-            float a_lo = 0.f, v_lo = 0.f, a_hi = 0.f, v_hi = 0.f;
-            float2 *p_lo = pc + pid_lo0, *p_hi = pc + pid_hi0;
-#pragma unroll
-            for (int j = 0; j < KP; ++j) {
-                const float a1 = lo_p[j];
-                float a2 = (j == 0) ? *hi0_p : hi_p[-j];
-                if (j == 0 && t == 0) a2 = 0.f;                  // "bin NC" does not exist
-                if (j > 0) {
-                    if (ctl & (1u << j)) { *p_lo = make_float2(a_lo, v_lo); ++p_lo; a_lo = v_lo = 0.f; }
-                    if (ctl & (1u << (16 + j))) { *p_hi = make_float2(a_hi, v_hi); --p_hi; a_hi = v_hi = 0.f; }
-                }
-                a_lo += a1; v_lo = fmaf(sw_t[j * G], a1, v_lo);
-                a_hi += a2; v_hi = fmaf(sw_t[(KP + 1 + j) * G], a2, v_hi);
-            }
-            {
-                const float a1 = (t == G - 1) ? *mid_p : 0.f;
-                if (ctl & (1u << KP)) { *p_lo = make_float2(a_lo, v_lo); ++p_lo; a_lo = v_lo = 0.f; }
-                a_lo += a1; v_lo = fmaf(sw_t[KP * G], a1, v_lo);
-            }
-            *p_lo = make_float2(a_lo, v_lo);
-            *p_hi = make_float2(a_hi, v_hi);
-        }
-        group_sync<0>();
-        // ---- channel c = t + G*i: (1-w) shares of the pieces of index c, w shares of the pieces of index c+1 -> the batch's row
-        {
-            float *mrow = melb + slot * MPITCH;
-            const uint32_t *rp = refs + t;
-            for (int i = 0; i < CPT; ++i) {
-                float su = 0.f, sv = 0.f;
-                for (int l = 0; l < LMAX; ++l) {
-                    const uint32_t r = rp[(i * LMAX + l) * G];
-                    const float2 pu = pc[r & 0xffffu], pv = pc[r >> 16];
-                    su += pu.x - pu.y;
-                    sv += pv.y;
-                }
-                const int c = t + G * i;
-                if (c < C) mrow[c] = su + sv;
-            }
-        }
-        // ---- Phase B at the end of a batch: one lane per frame ------------------------------------------------------------
-        if ((cons.j + 1) * FPW >= nfb) {
+        } else {
+            if (lane == 0) mbar_expect_tx(bar, (unsigned)(nf * W * 2));
             __syncwarp();
-            float acc[Geo::MAXCEP];
+            if (lane < nf) bulk_g2s(xs + lane * SLOT, src + (long)lane * hop, (unsigned)(W * 2), bar);
+        }
+    };
+    StridedDivmod dm((long)blockIdx.x, (long)gridDim.x, batches_per_utt), dn = dm;
+    if (warp == 0 && (long)blockIdx.x < n_batches) fetch(dm.q, dm.r);
+    unsigned phase = 0;
+
+    for (long batch = blockIdx.x; batch < n_batches; batch += gridDim.x, dm.next()) {
+        const int nfb = frames_in(dm.r);
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        // =================================== Phase A: |X| of this warp's frames ===================================
+        for (int j = 0; j * NGRP + warp * FPW < nfb; ++j) {
+            // ---- pre-emphasis (:208-210), window (:212-214): packed point n = t + G*m holds samples 2n, 2n+1 --------------
+            cf reg[E];
+            {
+                const uint32_t *fw = fw0 + j * ((NGRP * SLOT) / 2);
+                float carry = 0.f;     // thread 0: the odd sample of the last thread's previous point
 #pragma unroll
-            for (int i = 0; i < Geo::MAXCEP; ++i) acc[i] = 0.f;
-            if (lane < nfb) {
-                const float *mrow = melb + lane * MPITCH;
-                for (int c = 0; c < C; ++c) {
-                    const float lm = log_fast(mrow[c]);                                   // :170-172
-                    const float4 *d4 = reinterpret_cast<const float4 *>(dct + c * 16);   // same address in every lane: broadcast
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 d = d4[q];
-                        acc[4 * q] = fmaf(d.x, lm, acc[4 * q]); acc[4 * q + 1] = fmaf(d.y, lm, acc[4 * q + 1]);
-                        acc[4 * q + 2] = fmaf(d.z, lm, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(d.w, lm, acc[4 * q + 3]);
+                for (int m = 0; m < E; ++m) {
+                    if (m < MU) {
+                        const float2 x = s16x2_to_f32(fw[G * m]);
+                        const float up = __shfl_sync(0xffffffffu, x.y, (t + G - 1) & (G - 1), G);   // sample 2n-1 lives one thread down
+                        const float xm = (t == 0) ? carry : up;
+                        carry = up;
+                        const float2 w = win2[G * m];
+                        float2 v = __fmul2_rn(__ffma2_rn(make_float2(xm, x.x), make_float2(npre, npre), x), w);
+                        if (m == 0 && t == 0) v.x = 0.f;   // element 0 is never pre-emphasised: stays 0
+                        reg[m] = c2(v);
+                    } else {
+                        reg[m] = cmake<float>(0.f, 0.f);
                     }
                 }
             }
-            // rows through shared memory so that the batch leaves as one contiguous run (the exchange buffers are idle here)
+            // ---- packed real transform ------------------------------------------------------------------------------
+            group_fft<float, NC, E, false, 0>(reg, t, buf, tw);
+            // ---- |X| (:218-220) of the thread's bin pairs (k, NC-k), k = t + G*m; the mirrored bin lives in the partner thread -----
+            const float2 wtb = opaque(wt);
+            const int coff = j * NGRP;
 #pragma unroll
-            for (int i = 0; i < Geo::MAXCEP; ++i)
-                if (i < NCEP) obuf[lane * NCEP + i] = acc[i];
-            __syncwarp();
-            float *dst = a.feat + cons.d.q * feat_pitch + cons.d.r * FB * NCEP;
-            for (int i = lane; i < nfb * NCEP; i += 32) dst[i] = obuf[i];
-            __syncwarp();
+            for (int m = 0; m < HM; ++m) {
+                cf Bm;
+                Bm.x = __shfl_sync(0xffffffffu, reg[E - 1 - m].x, partner, G);
+                Bm.y = __shfl_sync(0xffffffffu, reg[E - 1 - m].y, partner, G);
+                if (t == 0) Bm = (m == 0) ? reg[0] : reg[E - m];     // thread 0 pairs with itself: bin NC - G*m is its own point E - m
+                const float2 cs = post_twiddle(wtb, m);
+                cf X1, X2;
+                untangle2x(reg[m], Bm, cs.x, cs.y, X1, X2);
+                mag_own[m * (G * MP) + coff] = sqrt_fast(X1.x * X1.x + X1.y * X1.y);
+                mag_mir[-m * (G * MP) + coff] = sqrt_fast(X2.x * X2.x + X2.y * X2.y);   // thread 0, m = 0: row of the unused "bin NC"
+            }
+            if (t == 0) {
+                cf X1, X2;
+                untangle2x(reg[HM], reg[HM], cs_half.x, cs_half.y, X1, X2);      // bin NC/2 (thread 0's point HM) pairs with itself
+                mag_mid[coff] = sqrt_fast(X1.x * X1.x + X1.y * X1.y);
+            }
+            __syncwarp();   // the exchange buffer is reused by the next step
         }
-        advance(cons);
-        cur ^= 1;
+        __syncthreads();   // the batch's magnitudes are complete; the PCM buffer and every exchange buffer are idle
+        if (warp == 0) {   // the next batch's PCM travels during Phase B
+            dn.next();
+            if (batch + gridDim.x < n_batches) fetch(dn.q, dn.r);
+        }
+        // =================================== Phase B ===================================
+        // ---- B1 MelFilterBank (:154-174), ln (:170-172): channel 4*warp + lane/8, frames 4*(lane%8) .. +3 ----------------------------
+        for (int c0 = 4 * warp; c0 < C; c0 += 4 * NW) {
+            const int c = c0 + (lane >> 3), q = lane & 7;
+            const int2 ct = chtab[c];
+            const int n = glen[c0 >> 2];
+            const float4 *xp = reinterpret_cast<const float4 *>(mag + ct.x * MP) + q;
+            const float *wp = tri + ct.y;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+            for (int k = 0; k < n; ++k) {
+                const float4 x = xp[k * (MP / 4)];
+                const float wgt = wp[k];
+                acc.x = fmaf(wgt, x.x, acc.x); acc.y = fmaf(wgt, x.y, acc.y);
+                acc.z = fmaf(wgt, x.z, acc.z); acc.w = fmaf(wgt, x.w, acc.w);
+            }
+            if (c < C)
+                *(reinterpret_cast<float4 *>(logmel + c * MP) + q) = make_float4(log_fast(acc.x), log_fast(acc.y), log_fast(acc.z), log_fast(acc.w));
+        }
+        __syncthreads();
+        // ---- B2 DCT (:176-183) x lifter (:185-192): cepstra CPW*warp .. CPW*warp+3 of frame `lane` ---------------------------------
+        if (warp * CPW < NCEP) {
+            float acc[CPW];
+#pragma unroll
+            for (int i = 0; i < CPW; ++i) acc[i] = 0.f;
+            const float4 *d4 = reinterpret_cast<const float4 *>(dct) + warp;
+            const float *lmp = logmel + lane;
+#pragma unroll 2
+            for (int c = 0; c < C; ++c) {
+                const float lm = lmp[c * MP];
+                const float4 d = d4[c * 4];                                  // same address in every lane: broadcast
+                acc[0] = fmaf(d.x, lm, acc[0]); acc[1] = fmaf(d.y, lm, acc[1]);
+                acc[2] = fmaf(d.z, lm, acc[2]); acc[3] = fmaf(d.w, lm, acc[3]);
+            }
+            if (lane < nfb) {
+                float *dst = a.feat + dm.q * feat_pitch + (dm.r * FB + lane) * NCEP + warp * CPW;
+#pragma unroll
+                for (int i = 0; i < CPW; ++i)
+                    if (warp * CPW + i < NCEP) dst[i] = acc[i];
+            }
+        }
+        // no barrier here: the next batch's Phase A touches the exchange buffers and mag, which B2 does not read, and its B1 rewrites
+        // logmel only after the barrier that follows that Phase A
     }
 }
 
