@@ -160,6 +160,40 @@ static int launch_c2c_cluster2(jdsp_ctx *c, const cx<float> *in, cx<float> *out,
 }
 #endif
 
+#ifndef JDSP_EMUL
+// N = N1 * N2 on clusters of C CTAs (kernels_fft.cuh: fft_c2c_cluster_kernel); the grid is as many whole clusters as can be resident.
+// Opt-in (JDSP_FFT_CLUSTER16=1).  Measured on B200 (profiles/round2/fft_cluster16_vs_default.txt): 0.55 / 0.38 / 0.34 of the HBM peak
+// at N = 2^14 / 2^15 / 2^16 against 0.72 / 0.45 / 0.44 for the default plans.  One HBM round trip with whole sectors on both sides
+// (DRAM traffic 1.00x algorithmic), but with 16 warps per SM the load, exchange (two cluster barriers), three barrier-separated
+// passes and the transposing store of a 64 KB tile run too much one after the other: issue slots 24 % busy, long-scoreboard 2.6,
+// mio-throttle 2.6 and barrier 1.7 stall cycles per issue (ncu_fft_cluster16_summary.txt).
+template <int N1, int N2, int C, bool INV>
+static int launch_c2c_cluster(jdsp_ctx *c, const cx<float> *in, cx<float> *out, long batch) {
+    using Geo = FftClusterGeom<N1, N2, C>;
+    void *t32, *twN;
+    TRY(get_table(c, 6, N2, &t32));
+    TRY(get_table(c, 3, N1 * N2, &twN));
+    auto kfn = fft_c2c_cluster_kernel<N1, N2, C, INV>;
+    TRY(opt_in_smem(kfn, Geo::SMEM));
+    if (C > 8) CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(Geo::THREADS); cfg.dynamicSmemBytes = Geo::SMEM; cfg.stream = c->stream; cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.gridDim = dim3((unsigned)(C * c->sm_count));
+    int max_clusters = 0;
+    CU(cudaOccupancyMaxActiveClusters(&max_clusters, kfn, &cfg));
+    if (max_clusters < 1) return fail(JDSP_ERR_CUDA, "cluster FFT kernel cannot be scheduled on this device");
+    if (const char *e = getenv("JDSP_FFT_CLUSTERS")) max_clusters = std::max(1, std::min(max_clusters, atoi(e)));
+    cfg.gridDim = dim3((unsigned)(C * std::min<long>(batch, max_clusters)));
+    const cx<float> *tw = (const cx<float> *)t32, *twn = (const cx<float> *)twN;
+    float one = 1.0f;
+    CU(cudaLaunchKernelEx(&cfg, kfn, in, out, batch, tw, twn, one));
+    return launch_check(c);
+}
+#endif
+
 template <typename T, int N1, int N2, bool INV>
 static int launch_c2c_fourstep(jdsp_ctx *c, const cx<T> *in, cx<T> *out, long batch, int tkind) {
     // 256-thread CTAs (3 per SM at 80 registers): the four barriers of a tile stall 8 warps instead of 16 and more tiles
@@ -253,17 +287,24 @@ static int fft_dispatch(jdsp_ctx *c, const cx<T> *in, cx<T> *out, int n, long ba
 #undef PIPE
 #undef SMALL
         case 16384:
+#ifndef JDSP_EMUL
+            if constexpr (sizeof(T) == 4) { if (getenv("JDSP_FFT_CLUSTER16")) return launch_c2c_cluster<16, 1024, 2, INV>(c, (const cx<float> *)in, (cx<float> *)out, batch); }
+#endif
             if constexpr (sizeof(T) == 4) { if (!getenv("JDSP_FFT_NO_BIG")) return launch_c2c_big<16384, INV>(c, (const cx<float> *)in, (cx<float> *)out, batch); }
             if constexpr (sizeof(T) == 4) { if (getenv("JDSP_FFT_FUSED")) return launch_c2c_fused<64, 256, INV>(c, in, out, batch); }
             return launch_c2c_fourstep<T, 64, 256, INV>(c, in, out, batch, tkind);
         case 32768:
 #ifndef JDSP_EMUL
+            if constexpr (sizeof(T) == 4) { if (getenv("JDSP_FFT_CLUSTER16")) return launch_c2c_cluster<16, 2048, 4, INV>(c, (const cx<float> *)in, (cx<float> *)out, batch); }
             if constexpr (sizeof(T) == 4) { if (getenv("JDSP_FFT_CLUSTER") && !getenv("JDSP_FFT_NO_SPLIT") && !getenv("JDSP_FFT_FUSED")) return launch_c2c_cluster2<16384, INV>(c, (const cx<float> *)in, (cx<float> *)out, batch); }
 #endif
             if constexpr (sizeof(T) == 4) { if (!getenv("JDSP_FFT_NO_SPLIT") && !getenv("JDSP_FFT_FUSED")) return launch_c2c_split2<16384, INV>(c, (const cx<float> *)in, (cx<float> *)out, batch); }
             if constexpr (sizeof(T) == 4) { if (getenv("JDSP_FFT_FUSED")) return launch_c2c_fused<128, 256, INV>(c, in, out, batch); }
             return launch_c2c_fourstep<T, 128, 256, INV>(c, in, out, batch, tkind);
         case 65536:
+#ifndef JDSP_EMUL
+            if constexpr (sizeof(T) == 4) { if (getenv("JDSP_FFT_CLUSTER16")) return launch_c2c_cluster<32, 2048, 8, INV>(c, (const cx<float> *)in, (cx<float> *)out, batch); }
+#endif
             if constexpr (sizeof(T) == 4) { if (getenv("JDSP_FFT_FUSED")) return launch_c2c_fused<256, 256, INV>(c, in, out, batch); }
             return launch_c2c_fourstep<T, 256, 256, INV>(c, in, out, batch, tkind);
         default: return fail(JDSP_ERR_UNSUPPORTED, "FFT length must be a power of two in [2, 65536]");

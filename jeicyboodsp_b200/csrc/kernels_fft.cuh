@@ -362,6 +362,115 @@ fft_c2c_cluster2_kernel(const cx<float> *__restrict__ in, cx<float> *__restrict_
 }
 #endif
 
+#ifndef JDSP_EMUL
+// ---- N = N1 * N2 on a cluster of C CTAs: ONE HBM round trip with full-sector accesses on both sides and ONE exchange through
+// distributed shared memory.  n = n2 + N2*n1, k = k1 + N1*k2:
+//   phase 1  CTA c owns the n2 range [c*N2/C, (c+1)*N2/C): a thread loads x[n2 + N2*n1], n1 < N1 (N1 coalesced loads), does the
+//            N1-point transform over n1 in registers and multiplies by W_N^(n2*k1) (rebuilt from log2(N1) table seeds);
+//   exchange value (k1, n2) goes to CTA k1/KPC (KPC = N1/C rows per CTA), straight from registers into that CTA's receive buffer
+//            (st.shared::cluster, lanes = consecutive n2: 256 contiguous bytes per warp instruction);
+//   phase 2  every CTA runs KPC transforms of N2 points over n2 on chip (32 points per thread, the receive buffer doubles as the
+//            exchange buffer), then writes X[k1 + N1*k2] for its KPC adjacent k1 as 8*KPC contiguous bytes per k2 (16-byte stores, two
+//            lanes per 32-byte sector).
+// 64 KB of shared memory and 256 threads per CTA: two CTAs of different clusters share an SM and overlap each other's load,
+// exchange and store phases (the 2-CTA version above had one 128 KB CTA per SM and ran its phases back to back).
+template <int N1, int N2, int C> struct FftClusterGeom {
+    static constexpr int E = 32, G2 = N2 / E, KPC = N1 / C, THREADS = KPC * G2, N = N1 * N2;
+    static constexpr int NPC = N2 / C, ROUNDS = NPC / THREADS;     // n2 values per CTA, phase-1 rounds per thread
+    static constexpr int LPK = KPC / 2 > 0 ? KPC / 2 : 1;          // lanes that write the 8*KPC bytes of one k2
+    static constexpr int PADN = padded_len_e<E>(N2);
+    static constexpr int ROWP = PADN + (LPK == 2 ? 4 : (LPK == 4 ? 2 : 0));   // row pitch: the LPK lanes of one k2 read LPK bank groups
+    static constexpr size_t SMEM = (size_t)KPC * ROWP * sizeof(cx<float>);
+    static_assert(N1 == 16 || N1 == 32, "first stage is one in-register DFT-16 / DFT-32 per thread");
+    static_assert(KPC >= 2 && N1 % C == 0 && NPC % THREADS == 0 && THREADS <= 1024 && PADN % 8 == 0, "geometry");
+};
+// W^k, k = 1 .. N1-1, from the seeds W^1, W^2, W^4, ... (each product is one level deep per set bit: <= 4e-7 relative)
+template <int N1> JDSP_DEV void twiddle_powers(cx<float> (&w)[N1], const cx<float> *__restrict__ twN, int q) {
+    w[0] = cmake<float>(1.f, 0.f);
+#pragma unroll
+    for (int b = 1; b < N1; b <<= 1) {
+        w[b] = twN[(long)q * b];
+#pragma unroll
+        for (int i = 1; i < b; ++i) w[b + i] = cmul<false>(w[i], w[b]);
+    }
+}
+template <int N1, int N2, int C, bool INV>
+__global__ void __launch_bounds__(FftClusterGeom<N1, N2, C>::THREADS, 2)
+fft_c2c_cluster_kernel(const cx<float> *__restrict__ in, cx<float> *__restrict__ out, long batch, const cx<float> *__restrict__ tw,
+                       const cx<float> *__restrict__ twN, float scale) {
+    using Geo = FftClusterGeom<N1, N2, C>;
+    constexpr int E = Geo::E, G2 = Geo::G2, KPC = Geo::KPC, NT = Geo::THREADS, N = Geo::N, NPC = Geo::NPC, ROUNDS = Geo::ROUNDS;
+    constexpr int ROWP = Geo::ROWP, LPK = Geo::LPK;
+    JDSP_DYN_SMEM(smem_raw);
+    cx<float> *recv = reinterpret_cast<cx<float> *>(smem_raw);
+    const int tid = threadIdx.x;
+    const unsigned rank = cluster_ctarank();
+    const long n_clusters = gridDim.x / C;
+    const int grp = tid / G2, t = tid % G2;            // phase 2: transform grp (k1 = rank*KPC + grp), lane t
+    cx<float> *buf = recv + grp * ROWP;
+    bool first = true;
+    for (long f = blockIdx.x / C; f < batch; f += n_clusters) {
+        const cx<float> *src = in + f * N;
+        // ---- phase 1 + exchange -----------------------------------------------------------------------------------------
+#pragma unroll 1
+        for (int r = 0; r < ROUNDS; ++r) {
+            const int n2 = (int)rank * NPC + r * NT + tid;
+            cx<float> v[N1];
+#pragma unroll
+            for (int i = 0; i < N1; ++i) v[i] = src[n2 + (long)N2 * i];
+            cx<float> w[N1];
+            twiddle_powers<N1>(w, twN, n2);
+            dftR<N1, INV>(v);
+#pragma unroll
+            for (int i = 1; i < N1; ++i) v[i] = cmul<INV>(v[i], w[i]);
+            if (r == 0 && !first) cluster_wait();      // every CTA of the cluster has emptied its receive buffer
+            const unsigned local = (unsigned)__cvta_generic_to_shared(recv + padE<E>(n2));
+#pragma unroll
+            for (int j = 0; j < C; ++j) {
+                unsigned base;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(base) : "r"(local), "r"(j));
+#pragma unroll
+                for (int k = 0; k < KPC; ++k) st_cluster(base + (unsigned)(k * ROWP * sizeof(cx<float>)), v[j * KPC + k]);
+            }
+        }
+        first = false;
+        cluster_arrive();
+        {   // pull this CTA's share of the cluster's next transform into L2 while the exchange settles and phase 2 runs
+            const long fn = f + n_clusters;
+            if (fn < batch) {
+                const char *nx = reinterpret_cast<const char *>(in + fn * N + (long)rank * NPC);
+                constexpr int LINES = NPC * (int)sizeof(cx<float>) / 128;     // per n1 row
+                for (int i = tid; i < N1 * LINES; i += NT) prefetch_l2(nx + (long)(i / LINES) * N2 * sizeof(cx<float>) + (long)(i % LINES) * 128);
+            }
+        }
+        cluster_wait();
+        // ---- phase 2: KPC transforms of N2 points, in place in the receive buffer --------------------------------------------
+        cx<float> reg[E];
+        fft_load_regs<float, N2, E>(reg, t, buf);
+        __syncthreads();
+        const cx<float> *twp = tw;
+        asm volatile("" : "+l"(twp)::"memory");
+        group_fft<float, N2, E, INV, 1>(reg, t, buf, twp);
+        __syncthreads();
+        fft_store_regs<float, N2, E>(reg, t, buf);
+        __syncthreads();
+        // ---- X[k1 + N1*k2], k1 = rank*KPC .. +KPC-1: lane pairs (quads) cover the 8*KPC contiguous bytes of one k2 -------------------
+        {
+            float4 *dst = reinterpret_cast<float4 *>(out + f * N + (long)rank * KPC);
+            constexpr int ITEMS = N2 * LPK;
+#pragma unroll 4
+            for (int it = tid; it < ITEMS; it += NT) {
+                const int k2 = it / LPK, h = it % LPK;
+                const cx<float> a = recv[(2 * h) * ROWP + padE<E>(k2)], b = recv[(2 * h + 1) * ROWP + padE<E>(k2)];
+                dst[(long)k2 * (N1 / 2) + h] = make_float4(a.x * scale, a.y * scale, b.x * scale, b.y * scale);
+            }
+        }
+        cluster_arrive();     // "my receive buffer is free again": matched by the wait before the next remote stores
+    }
+    if (!first) cluster_wait();   // nobody leaves while a peer may still be counting on this CTA's barrier arrival
+}
+#endif
+
 // ---- four-step for N = N1 * N2 (both handled by one thread group each) -----------------------------------
 // Step A: for CT adjacent columns n2, DFT over n1 (stride N2), multiply by W_N^(n2*k1), write row-major [k1][n2].
 // Global accesses are CT*sizeof(cx) contiguous bytes per row; all loads of a tile are issued before the first

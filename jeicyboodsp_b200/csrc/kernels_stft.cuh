@@ -182,13 +182,15 @@ __global__ void __launch_bounds__(RoundtripGeom<N>::THREADS) roundtrip_kernel(Ro
 // One spectral bin of D2 + D3/D4, shared by both denoise kernels so that they produce identical bits: noise average /
 // publish (:182-193), then Y = gain * X with the 1/N of the inverse transform folded into the gain.  nss holds ns/N (SS) or
 // ns^2/N (Wiener).  cbits: bit0 update, bit1 halve, bit2 publish.  UPD: 0 = never update, 1 = always, 2 = when cbits != 0.
-// X.x carries a +1e-15 bias so that X = 0 behaves like the reference's atan2(0,0) = 0: |X| - ns along +1 gives (-ns, 0)
-// (appendix C-7); the bias is below half an ulp of any non-zero bin of an int16 frame, so it changes nothing else.
+// X = 0 must behave like the reference's atan2(0,0) = 0: |X| - ns along +1 gives (-ns, 0) (appendix C-7).  Exact zeros only come
+// from all-zero frames, so the callers add 1e-15 to the frame's sample 0 (packed point 0, real lane): in an all-zero frame every
+// bin then is a tiny positive real number and the formulas below give (-ns, 0) without a compare; in any other frame the bump is
+// far below half an ulp of the sample (the Hamming window is 0.08 there) or of every bin, and changes nothing.  The 2e-38 keeps
+// rsqrt finite should a single bin cancel to exactly 0 (that bin then gives 0, not (-ns, 0)).
 template <int MODE, int UPD>
 JDSP_DEV cf denoise_bin(cf X, unsigned cbits, float inv_n, float &avg, float &nss) {
-    X.x += 1e-15f;
-    const float p = X.x * X.x + X.y * X.y;
-    const float r = rsqrt_fast(fmaxf(p, 1e-30f));
+    const float p = fmaf(X.x, X.x, fmaf(X.y, X.y, 2e-38f));
+    const float r = rsqrt_fast(p);
     if (UPD == 1 || (UPD == 2 && cbits != 0u)) {
         avg += p * r;                                                      // :183  |X| = p * rsqrt(p)
         if (cbits & 2u) avg *= 0.5f;                                       // :184-186
@@ -389,6 +391,7 @@ __global__ void __launch_bounds__(DenoiseGeom<NC, F>::NT, NC == 256 ? 6 : 3) den
                     const float2 w = w2[t + G * m];
                     reg[m] = c2(__fmul2_rn(make_float2(s16lo(wd), s16hi(wd)), w));
                 }
+                if (t == 0) reg[0].x += 1e-15f;   // see denoise_bin
             }
             if constexpr (REGTW) group_fft_regtw<float, NC, E, false, 0>(reg, t, buf, twv);
             else group_fft<float, NC, E, false, 0>(reg, t, buf, tw);

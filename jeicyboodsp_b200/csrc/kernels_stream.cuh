@@ -104,7 +104,13 @@ template <int NC, int MODE, int E_ = 16>
 __global__ void __maxnreg__((StreamGeom<NC, E_>::MAXREG)) denoise_stream_kernel(DenoiseArgs a) {
     using Geo = StreamGeom<NC, E_>;
     constexpr int N = Geo::N, H = Geo::H, E = Geo::E, G = Geo::G, NT = Geo::NT, GPC = Geo::GPC, HM = E / 2;
-    constexpr int MSTRIDE = G + G / 16;                   // padded distance between a thread's consecutive points
+    // The mirror exchange uses the exchange buffer WITHOUT padding: a group writes / reads 16 (32) consecutive elements per
+    // instruction either way, so plain addresses are conflict-free, whereas the padded ones put element NC - G*m (thread 0) and
+    // element NC - G*m - 15 (thread 15) 16 slots apart: a 2-way conflict on every access of the exchange (10 % of the kernel's
+    // shared-memory wavefronts, found with the per-line wavefront counts of tools/ncu_lines.py): 218 -> 202 wavefronts per frame,
+    // 2.20 -> 2.14 ms per 4096 x 8 s.  (The warp-wide groups of the pitch kernel -- G = 32 -- measured 7 % SLOWER without the padding,
+    // 6.08 -> 6.51 ms per 4096 x 20 s on the same box, and keep it; so does the MVDR apply kernel.)
+    constexpr int MSTRIDE = G;                            // distance between a thread's consecutive points
     JDSP_DYN_SMEM(smem_raw);
     cf *fbuf = reinterpret_cast<cf *>(smem_raw + Geo::OFF_FBUF);
     double *wvad = reinterpret_cast<double *>(smem_raw + Geo::OFF_WVAD);
@@ -134,8 +140,9 @@ __global__ void __maxnreg__((StreamGeom<NC, E_>::MAXREG)) denoise_stream_kernel(
     const bool want_f32 = a.out_f32 != nullptr && live, want_vad = a.vad != nullptr && live;
 
     cf *buf = fbuf + g * Geo::GBUF;
-    cf *own = buf + pad16(t);                  // point t + G*m at own[m * MSTRIDE]
-    cf *mir = buf + pad16(NC - t);             // point NC - (t + G*m) at mir[-m * MSTRIDE]; slot PADN stands in for "bin NC" = bin 0
+    cf *own = buf + t;                         // point t + G*m at own[m * MSTRIDE]
+    cf *mir = buf + (NC - t);                  // point NC - (t + G*m) at mir[-m * MSTRIDE]; slot NC stands in for "bin NC" = bin 0
+    const float bias0 = (t == 0) ? 1e-15f : 0.f;   // see denoise_bin
     const float2 *win2 = reinterpret_cast<const float2 *>(winh) + t;
     const double2 *wv2 = reinterpret_cast<const double2 *>(wvad) + t;
     const float2 *twr_t = twr + t;
@@ -234,6 +241,7 @@ __global__ void __maxnreg__((StreamGeom<NC, E_>::MAXREG)) denoise_stream_kernel(
 #pragma unroll
         for (int m = 0; m < HM; ++m) {
             reg[m] = c2(__fmul2_rn(f2(prevf[m]), win2[G * m]));
+            if (m == 0) reg[0].x += bias0;
             const cf xf = cmake<float>(s16lo(wc[m]), s16hi(wc[m]));
             reg[m + HM] = c2(__fmul2_rn(f2(xf), win2[G * (m + HM)]));
             prevf[m] = xf;
@@ -244,7 +252,7 @@ __global__ void __maxnreg__((StreamGeom<NC, E_>::MAXREG)) denoise_stream_kernel(
         group_sync<0>();
 #pragma unroll
         for (int m = HM; m < E; ++m) own[m * MSTRIDE] = reg[m];
-        if (t == 0) buf[Geo::PADN] = reg[0];
+        if (t == 0) buf[NC] = reg[0];
         group_sync<0>();
         const float2 cs_half = twr[NC / 2];
         if (cbits) denoise_bins<MODE, true, E, G, MSTRIDE, NT>(reg, mir, twr_t, cs_half, cbits, inv_n, avgp, nss1, nss2, avgS, nssS);

@@ -72,6 +72,7 @@ def test_fft_c2c_f32_persistent_loops(be, n):
                                         ("JDSP_FFT_NO_BIG,JDSP_FFT_NO_PIPE", (2048, 4096, 8192)),   # the plain on-chip kernel
                                         ("JDSP_FFT_NO_BIG,JDSP_FFT_FUSED", (16384, 32768, 65536)),  # one persistent four-step kernel
                                         ("JDSP_FFT_CLUSTER", (32768,)),     # 2-CTA cluster with a DSMEM swap (GPU only; the emulator keeps the split kernel)
+                                        ("JDSP_FFT_CLUSTER16", (16384, 32768, 65536)),   # first stage in registers, one DSMEM exchange, clusters of 2 / 4 / 8
                                         ("JDSP_FFT_NO_SPLIT", (32768,))])   # the two-kernel four-step instead of the radix-2 split over the on-chip 16384 kernel
 def test_fft_alternate_plans(be, monkeypatch, plan, sizes):
     """The measured-and-kept-as-fallback FFT plans stay correct (they are selected by environment variables only)."""
