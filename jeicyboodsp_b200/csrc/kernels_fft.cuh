@@ -2,9 +2,13 @@
 //
 // Replaces FFTProcess + Bitrev (FFTAlgorithm_ver2.cpp:94-149,186-207) for arbitrary batches.
 // Unnormalised in both directions like the reference (:75-80 divides by N in the caller).
-//   N <= 8192 : one thread group per transform, whole transform on chip, one HBM read + one write.
-//   N >= 16384: four-step (N = N1*N2) as two kernels over a scratch buffer (two HBM round trips; an
-//               L2-resident chunking was measured slower because the per-launch ramp dominates).
+//   N <= 1024        : fft_c2c_kernel -- several transforms per CTA, points straight between global memory and registers.
+//   N = 2048         : fft_c2c_pipe_kernel -- persistent CTAs, the next transform bulk-copied (TMA) while this one is computed.
+//   N = 4096..16384  : fft_c2c_big_kernel -- 32 points per thread, whole transform on chip, next transform prefetched into L2.
+//   N = 32768        : fft_c2c_split2_kernel -- one radix-2 step folded into the load of the on-chip 16384 kernel (one HBM round trip).
+//   N = 65536, fp64 N >= 16384 : fft_cols_kernel + fft_rows_kernel -- four-step over a scratch buffer (two HBM round trips).
+//   Opt-in, measured slower and kept as cross-checks: fft_fourstep_fused_kernel (JDSP_FFT_FUSED), fft_c2c_cluster2_kernel
+//   (JDSP_FFT_CLUSTER), fft_c2c_cluster_kernel (JDSP_FFT_CLUSTER16); jdsp_api.cu:fft_dispatch holds the plan table.
 #pragma once
 #include "jdsp_device.cuh"
 
