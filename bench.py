@@ -325,7 +325,7 @@ def cfg_fastconv(B: Bench):
     res = {"name": "fastconv", "workload": f"BASELINE.json configs[2]: {S_total} sources x {n / 48000:.0f} s @ 48 kHz x 512-tap HRIR pair -> binaural "
                                            f"(overlap-save, n_fft 1024, block 512; mode A: one output pair per source), {S} sources on this rank",
            "scaling": "strong", "unit": "Msamples/s (input samples)", "value": S_total * n / ms / 1e3, "ms": ms, "ms_best": best,
-           "roofline": _roof("jdsp::fastconv_kernel", alg, ms, FLOP_PER_SAMPLE["fastconv"] * S * n,
+           "roofline": _roof("jdsp::fastconv_stream_kernel<512>", alg, ms, FLOP_PER_SAMPLE["fastconv"] * S * n,
                              "6 B per input sample (int16 in, two int16 ears out); filter spectra stay on chip")}
     if B.rank == 0 and not args.no_parity:
         run(); torch.cuda.synchronize()
@@ -566,7 +566,7 @@ def cfg_roundtrip(B: Bench):
                                             f"{R_total} replicas ({R} on this rank) for the roofline; the single stream for latency",
            "scaling": "strong", "unit": "Msamples/s", "value": R_total * row / ms / 1e3, "ms": ms, "ms_best": best,
            "single_stream_us": ms1 * 1e3, "single_stream_msamples_s": row / ms1 / 1e3,
-           "roofline": _roof("jdsp::roundtrip_kernel<1024>", alg, ms, FLOP_PER_SAMPLE["roundtrip"] * R * row, "4 B per sample (int16 in + int16 out)")}
+           "roofline": _roof("jdsp::roundtrip_warp_kernel<1024>", alg, ms, FLOP_PER_SAMPLE["roundtrip"] * R * row, "4 B per sample (int16 in + int16 out)")}
     if B.rank == 0 and not args.no_parity:
         f32 = torch.empty((1, row), dtype=torch.float32, device=dev)
         B.ctx.roundtrip_dev(one, row, y, row, f32, row, n_fft, 1, nb)

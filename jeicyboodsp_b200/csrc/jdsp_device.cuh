@@ -286,17 +286,53 @@ template <typename T, int NC, int E> JDSP_DEV void fft_store_regs(const cx<T> (&
 // Whole transform.  In: reg[m] = x[t + G*m].  Out: reg[m] = X[t + G*m] (natural order).
 // buf: padded_len(NC) elements of shared memory private to the group; may hold garbage on entry but
 // nobody else may be reading it.  SYNC 0: the group lives inside one warp; 1: the group is the CTA.
-template <typename T, int NC, int E, bool INV, int SYNC, int NS = 1>
+// Final radix-2 pass of a warp-wide transform (G = 32 lanes, NC = 2*16*E... = 32*E points) across the lane pairs (t, t ^ 16) by
+// shuffles instead of one more shared-memory exchange.  On entry reg[i] is output i of the pass with NS = NC/32, R = 16, i.e. the
+// sequence element 256*(t/16) + t%16 + 16*i (for NC = 512): lanes t < 16 hold the lower halves s[j] of the butterflies
+// (j, j + NC/2), j = t + 16*i, lanes t >= 16 the upper halves.  Lane t must end with X[t + 32*m] and X[t + 32*m + NC/2], the
+// butterflies j = t + 32*m: even i for the low lanes, odd i for the high lanes, so a low lane sends its odd outputs and a high
+// lane its even ones: 16 shuffle cycles of the shared-memory data pipe instead of the 64 of a 64-bit store + load exchange (the
+// pipe that bounds the 512-point frame kernels), paid with 6 selects per butterfly.
+template <typename T, int NC, int E, bool INV>
+JDSP_DEV void fft_last_radix2_shfl(cx<T> (&reg)[E], int t, const cx<T> *__restrict__ tw) {
+    static_assert(NC == 32 * E && E == 16, "warp-wide 512-point transform, 16 points per thread");
+    constexpr int TWOFF = TwLayout<NC, E>::offset(NC / 2);
+    const cx<T> *twp = tw + TWOFF + t;
+    const bool lo = t < 16;
+    cx<T> out[E];
+#pragma unroll
+    for (int m = 0; m < E / 2; ++m) {
+        const cx<T> ev = reg[2 * m], od = reg[2 * m + 1];
+        cx<T> send, got;
+        send.x = lo ? od.x : ev.x; send.y = lo ? od.y : ev.y;
+        got.x = __shfl_xor_sync(0xffffffffu, send.x, 16);
+        got.y = __shfl_xor_sync(0xffffffffu, send.y, 16);
+        cx<T> a, b;
+        a.x = lo ? ev.x : got.x; a.y = lo ? ev.y : got.y;
+        b.x = lo ? got.x : od.x; b.y = lo ? got.y : od.y;
+        b = cmul<INV>(b, twp[32 * m]);
+        out[m] = cadd(a, b);
+        out[m + E / 2] = csub(a, b);
+    }
+#pragma unroll
+    for (int m = 0; m < E; ++m) reg[m] = out[m];
+}
+
+template <typename T, int NC, int E, bool INV, int SYNC, int NS = 1, bool SHFL_LAST = false>
 JDSP_DEV void group_fft(cx<T> (&reg)[E], int t, cx<T> *buf, const cx<T> *__restrict__ tw) {
     constexpr int REM = NC / NS;
     constexpr int R = REM < E ? REM : E;
     fft_pass_compute<T, NC, E, R, NS, INV>(reg, t, tw);
     if constexpr (NS * R < NC) {
-        if constexpr (NS > 1) group_sync<SYNC>();  // every thread has finished loading before anyone overwrites
-        fft_pass_store<T, NC, E, R, NS>(reg, t, buf);
-        group_sync<SYNC>();
-        fft_load_regs<T, NC, E>(reg, t, buf);
-        group_fft<T, NC, E, INV, SYNC, NS * R>(reg, t, buf, tw);
+        if constexpr (SHFL_LAST && NS * R * 2 == NC) {
+            fft_last_radix2_shfl<T, NC, E, INV>(reg, t, tw);
+        } else {
+            if constexpr (NS > 1) group_sync<SYNC>();  // every thread has finished loading before anyone overwrites
+            fft_pass_store<T, NC, E, R, NS>(reg, t, buf);
+            group_sync<SYNC>();
+            fft_load_regs<T, NC, E>(reg, t, buf);
+            group_fft<T, NC, E, INV, SYNC, NS * R, SHFL_LAST>(reg, t, buf, tw);
+        }
     }
 }
 

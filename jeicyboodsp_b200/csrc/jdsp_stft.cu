@@ -15,6 +15,24 @@ template <int N> static int launch_roundtrip(jdsp_ctx *c, RoundtripArgs a) {
     return launch_check(c);
 }
 
+// N = 512 / 1024: 32 points per thread, one thread group per block pair (JDSP_ROUNDTRIP_CTA=1 keeps the CTA-staged kernel)
+template <int N> static int launch_roundtrip_warp(jdsp_ctx *c, RoundtripArgs a) {
+    using Geo = RoundtripWarpGeom<N>;
+    void *t32;
+    TRY(get_table(c, 6, N, &t32));
+    a.tw = (const cf *)t32;
+    auto kfn = roundtrip_warp_kernel<N>;
+    TRY(opt_in_smem(kfn, Geo::SMEM));
+    int per_sm = 4;
+#ifndef JDSP_EMUL
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, Geo::NT, Geo::SMEM));
+    if (per_sm < 1) return fail(JDSP_ERR_CUDA, "round-trip kernel does not fit an SM");
+#endif
+    const long items = a.n_streams * ((a.n_blocks + 1) / 2);
+    JDSP_LAUNCH_PTR(kfn, dim3(grid_for(c, (items + Geo::GPC - 1) / Geo::GPC, per_sm)), dim3(Geo::NT), Geo::SMEM, c->stream, a);
+    return launch_check(c);
+}
+
 extern "C" {
 int jdsp_roundtrip_i16_dev(jdsp_ctx *c, const int16_t *d_in, long in_pitch, int16_t *d_out, long out_pitch, float *d_out_f32,
                            long f32_pitch, int n_fft, long n_streams, long n_blocks) {
@@ -31,8 +49,8 @@ int jdsp_roundtrip_i16_dev(jdsp_ctx *c, const int16_t *d_in, long in_pitch, int1
         case 64: return launch_roundtrip<64>(c, a);
         case 128: return launch_roundtrip<128>(c, a);
         case 256: return launch_roundtrip<256>(c, a);
-        case 512: return launch_roundtrip<512>(c, a);
-        case 1024: return launch_roundtrip<1024>(c, a);
+        case 512: return getenv("JDSP_ROUNDTRIP_CTA") ? launch_roundtrip<512>(c, a) : launch_roundtrip_warp<512>(c, a);
+        case 1024: return getenv("JDSP_ROUNDTRIP_CTA") ? launch_roundtrip<1024>(c, a) : launch_roundtrip_warp<1024>(c, a);
         case 2048: return launch_roundtrip<2048>(c, a);
         case 4096: return launch_roundtrip<4096>(c, a);
         default: return fail(JDSP_ERR_UNSUPPORTED, "round trip supports n_fft = 64..4096 (power of two)");

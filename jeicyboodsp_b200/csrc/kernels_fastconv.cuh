@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(FastconvStreamGeom<NC>::NT, 4) fastconv_stream
                 reg[m] = c2(s16x2_to_f32(wp[m]));
                 reg[m + HM] = c2(s16x2_to_f32(wc[m]));
             }
-            group_fft<float, NC, E, false, 0>(reg, t, ebuf, tw);
+            group_fft<float, NC, E, false, 0, 1, NC == 512>(reg, t, ebuf, tw);
             // ---- real spectrum of this thread's bin pairs (k, NC-k), k = t + G*m: the mirrored bin lives in the partner thread
             cf X1[HM], X2[HM], XS;
 #pragma unroll
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(FastconvStreamGeom<NC>::NT, 4) fastconv_stream
                     carry = zm;
                 }
                 group_sync<0>();      // the exchange buffer: everybody is past the previous transform's last loads
-                group_fft<float, NC, E, true, 0>(reg, t, ebuf, tw);
+                group_fft<float, NC, E, true, 0, 1, NC == 512>(reg, t, ebuf, tw);
                 // ---- out[i] = (short) y[i + n_taps - 1] (:156-158): the last B samples of the window = points HM.. of every thread
                 if (valid && blk >= 0) {
                     uint32_t *op = reinterpret_cast<uint32_t *>(a.out + (src * NE + ear) * out_pitch) + blk * (B / 2) + t;

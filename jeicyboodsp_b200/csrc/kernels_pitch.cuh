@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(PitchGeom<NC>::NT) pitch_kernel(PitchArgs a) {
             reg[m] = cmake<float>(0.5f * s16lo(wp), 0.5f * s16hi(wp));
             reg[m + HM] = cmake<float>(0.5f * s16lo(wc), 0.5f * s16hi(wc));
         }
-        group_fft<float, NC, E, false, 0>(reg, t, buf, tw);
+        group_fft<float, NC, E, false, 0, 1, NC == 512>(reg, t, buf, tw);
         // ---- |X|^2 / N on bin pairs (k, NC-k) (:90-93), straight back into the packed inverse ----------------------------
         group_sync<0>();
 #pragma unroll
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(PitchGeom<NC>::NT) pitch_kernel(PitchArgs a) {
             if (t != 0) reg[HM] = z8;
         }
         group_sync<0>();
-        group_fft<float, NC, E, true, 0>(reg, t, buf, tw);   // reg[m] = (r[2n], r[2n+1]), n = t + G*m  (:94-97)
+        group_fft<float, NC, E, true, 0, 1, NC == 512>(reg, t, buf, tw);   // reg[m] = (r[2n], r[2n+1]), n = t + G*m  (:94-97)
         // ---- screen: every lag in (min_lag, H) whose fp32 value is within the error band of the fp32 maximum -------------
         const float r0 = __shfl_sync(0xffffffffu, reg[0].x, 0);   // r[0] = sum x^2 >= |r[i]|
         float vmax = -3.0e38f;

@@ -25,6 +25,16 @@ JDSP_DEV float2 s16x2_to_f32(uint32_t w) {
     return __fadd2_rn(make_float2(lo, hi), make_float2(-8421376.0f, -8421376.0f));
 #endif
 }
+// one MUFU.RCP, no denormal fix-up sequence; callers keep the argument away from 0
+JDSP_DEV float rcp_fast(float x) {
+#ifdef JDSP_EMUL
+    return 1.0f / x;
+#else
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#endif
+}
 // one MUFU.RSQ, no denormal fix-up sequence; callers clamp the argument away from 0
 JDSP_DEV float rsqrt_fast(float x) {
 #ifdef JDSP_EMUL
@@ -179,6 +189,80 @@ __global__ void __launch_bounds__(RoundtripGeom<N>::THREADS) roundtrip_kernel(Ro
     }
 }
 
+// ---- Round trip at N = 512 / 1024 with 32 points per thread: one thread GROUP (a half warp / a warp) per block pair, two passes
+// (32 x 16 / 32 x 32) and ONE shared-memory exchange per transform instead of three passes and two exchanges, samples straight
+// between global memory and registers, no CTA barrier.  The 16-points-per-thread kernel above is bound by the shared-memory data
+// pipe (two exchanges per transform, staging in and out, 16-bit accesses: ~900 pipe cycles per block pair at N = 1024; this one
+// ~380), which is why fewer resident warps at 32 points per thread now pay off.
+template <int N>
+struct RoundtripWarpGeom {
+    static constexpr int E = 32, G = N / E, WARPS = 4, NT = WARPS * 32, GPC = NT / G;   // GPC block pairs in flight per CTA
+    static constexpr int PADN = padded_len_e<E>(N);
+    static constexpr int NTW = TwLayout<N, E>::total;
+    static constexpr size_t OFF_TW = (size_t)GPC * PADN * sizeof(cf);
+    static constexpr size_t SMEM = OFF_TW + (size_t)NTW * sizeof(cf);
+    static_assert(G == 16 || G == 32, "a block pair is handled by a half warp or a warp");
+};
+template <int N>
+__global__ void __launch_bounds__(RoundtripWarpGeom<N>::NT, 4) roundtrip_warp_kernel(RoundtripArgs a) {
+    using Geo = RoundtripWarpGeom<N>;
+    constexpr int E = Geo::E, G = Geo::G, NT = Geo::NT, GPC = Geo::GPC;
+    JDSP_DYN_SMEM(smem_raw);
+    cf *tw = reinterpret_cast<cf *>(smem_raw + Geo::OFF_TW);
+    for (int i = threadIdx.x; i < Geo::NTW; i += NT) tw[i] = a.tw[i];
+    __syncthreads();
+    const int grp = threadIdx.x / G, t = threadIdx.x % G;
+    cf *buf = reinterpret_cast<cf *>(smem_raw) + grp * Geo::PADN;
+    const long pairs_per_stream = (a.n_blocks + 1) / 2;
+    const long n_items = a.n_streams * pairs_per_stream;
+    const long warp_items = (n_items + (32 / G) - 1) / (32 / G);          // items are dealt to whole warps so that warp-level syncs stay whole
+    const float inv_n = 1.0f / (float)N;
+    const long wstride = (long)gridDim.x * Geo::WARPS;
+    const long w0 = (long)blockIdx.x * Geo::WARPS + threadIdx.x / 32;
+    StridedDivmod dm(w0 * (32 / G) + (threadIdx.x % 32) / G, wstride * (32 / G), pairs_per_stream);
+    for (long wi = w0; wi < warp_items; wi += wstride, dm.next()) {
+        const long item = wi * (32 / G) + (threadIdx.x % 32) / G;
+        const bool live = item < n_items;                                 // a dead half warp shadows the last item and stores nothing
+        const long s = live ? dm.q : a.n_streams - 1, pr = live ? dm.r : pairs_per_stream - 1;
+        const bool two = 2 * pr + 1 < a.n_blocks;                         // an odd block count leaves the last pair with one block
+        const int16_t *pa = a.in + s * a.in_pitch + 2 * pr * (long)N + t;
+        const int16_t *pb = two ? pa + N : pa;
+        cf reg[E];
+#pragma unroll
+        for (int m = 0; m < E; ++m) reg[m] = cmake<float>(__int2float_rn((int)pa[G * m]), __int2float_rn((int)pb[G * m]));
+        if (!two) {
+#pragma unroll
+            for (int m = 0; m < E; ++m) reg[m].y = 0.f;
+        }
+        const cf *twp = tw;
+#ifndef JDSP_EMUL
+        asm volatile("" : "+l"(twp)::"memory");   // keep the twiddle loads of the second pass below the 64 sample loads (register pressure)
+#endif
+        group_sync<0>();                          // the previous item's inverse transform has been read out of the exchange buffer
+        group_fft<float, N, E, false, 0>(reg, t, buf, twp);
+        group_sync<0>();
+        group_fft<float, N, E, true, 0>(reg, t, buf, twp);
+        if (live) {
+            const long o0 = 2 * pr * (long)N + t;
+            int16_t *qa = a.out + s * a.out_pitch + o0;
+#pragma unroll
+            for (int m = 0; m < E; ++m) qa[G * m] = trunc16(reg[m].x * inv_n);       // FFTAlgorithm_ver2.cpp:80
+            if (two) {
+#pragma unroll
+                for (int m = 0; m < E; ++m) qa[N + G * m] = trunc16(reg[m].y * inv_n);
+            }
+            if (a.out_f32) {
+                float *fa = a.out_f32 + s * a.f32_pitch + o0;
+#pragma unroll
+                for (int m = 0; m < E; ++m) {
+                    fa[G * m] = reg[m].x * inv_n;
+                    if (two) fa[N + G * m] = reg[m].y * inv_n;
+                }
+            }
+        }
+    }
+}
+
 // One spectral bin of D2 + D3/D4, shared by both denoise kernels so that they produce identical bits: noise average /
 // publish (:182-193), then Y = gain * X with the 1/N of the inverse transform folded into the gain.  nss holds ns/N (SS) or
 // ns^2/N (Wiener).  cbits: bit0 update, bit1 halve, bit2 publish.  UPD: 0 = never update, 1 = always, 2 = when cbits != 0.
@@ -190,15 +274,17 @@ __global__ void __launch_bounds__(RoundtripGeom<N>::THREADS) roundtrip_kernel(Ro
 template <int MODE, int UPD>
 JDSP_DEV cf denoise_bin(cf X, unsigned cbits, float inv_n, float &avg, float &nss) {
     const float p = fmaf(X.x, X.x, fmaf(X.y, X.y, 2e-38f));
-    const float r = rsqrt_fast(p);
+    // SS needs 1/|X| (and |X| = p / |X| for the noise average), Wiener 1/|X|^2: one MUFU either way; Wiener's noise-update blocks
+    // (the only ones that need |X| as well) pay a second one
+    const float r = MODE == 0 ? rsqrt_fast(p) : rcp_fast(p);
     if (UPD == 1 || (UPD == 2 && cbits != 0u)) {
-        avg += p * r;                                                      // :183  |X| = p * rsqrt(p)
+        avg += MODE == 0 ? p * r : p * rsqrt_fast(p);                      // :183  |X| = p * rsqrt(p)
         if (cbits & 2u) avg *= 0.5f;                                       // :184-186
         if (cbits & 4u) nss = (MODE == 0 ? avg : avg * avg) * inv_n;       // :189-193
     }
     float g;
     if (MODE == 0) g = fmaf(-nss, r, inv_n);                               // amp = |X| - ns, no floor (:238)
-    else g = inv_n - fminf(nss * (r * r), inv_n);                          // WienerFilter_final.cpp:204-208
+    else g = fmaxf(fmaf(-nss, r, inv_n), 0.f);                             // WienerFilter_final.cpp:204-208: 1/N - min(ns^2/|X|^2, 1)/N
     return cmake<float>(X.x * g, X.y * g);
 }
 
