@@ -11,7 +11,9 @@
 //   * the per-bin stage works on the transform's own registers: bins k < NC/2 stay with their thread, the
 //     mirrored bins NC-k come from / go back to the partner thread through one small shared-memory exchange.
 // Shared memory carries only the Stockham exchange of each transform, that mirror exchange, and the tables.
-// (Round 2 measured the mirror exchange by shuffles and the post-twiddles rebuilt from a per-thread seed instead of the table:
+// (Round 2 measured the mirror exchange by shuffles on its own, after the exchange had lost its bank conflicts: 16 data-pipe cycles
+// per frame fewer, 14 instructions per frame more (thread 0's selects), 4 bytes of spills: 6.5 % SLOWER, 2.29 / 2.34 ms against
+// 2.15 / 2.17 ms per 4096 x 8 s on the same box.  Earlier, together with the post-twiddles rebuilt from a per-thread seed instead of the table:
 // 13 % fewer shared-memory wavefronts, ~4 % more packed arithmetic, 20-40 bytes of spills at the 128-register cap -- 9 % SLOWER,
 // 17.8 / 18.7 ms against 16.3 / 16.8 ms per pass; the kernel is bound by issue slots and the fp32 pipe, not by shared memory.)
 #pragma once
