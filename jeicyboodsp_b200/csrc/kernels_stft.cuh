@@ -25,6 +25,14 @@ JDSP_DEV float2 s16x2_to_f32(uint32_t w) {
     return __fadd2_rn(make_float2(lo, hi), make_float2(-8421376.0f, -8421376.0f));
 #endif
 }
+// pull one 128-byte line into L2 ahead of use
+JDSP_DEV void prefetch_l2_line(const void *p) {
+#ifndef JDSP_EMUL
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
 // one MUFU.RCP, no denormal fix-up sequence; callers keep the argument away from 0
 JDSP_DEV float rcp_fast(float x) {
 #ifdef JDSP_EMUL
@@ -219,7 +227,7 @@ __global__ void __launch_bounds__(RoundtripWarpGeom<N>::NT, 4) roundtrip_warp_ke
     const float inv_n = 1.0f / (float)N;
     const long wstride = (long)gridDim.x * Geo::WARPS;
     const long w0 = (long)blockIdx.x * Geo::WARPS + threadIdx.x / 32;
-    StridedDivmod dm(w0 * (32 / G) + (threadIdx.x % 32) / G, wstride * (32 / G), pairs_per_stream);
+    StridedDivmod dm(w0 * (32 / G) + (threadIdx.x % 32) / G, wstride * (32 / G), pairs_per_stream), dn = dm;
     for (long wi = w0; wi < warp_items; wi += wstride, dm.next()) {
         const long item = wi * (32 / G) + (threadIdx.x % 32) / G;
         const bool live = item < n_items;                                 // a dead half warp shadows the last item and stores nothing
@@ -227,6 +235,15 @@ __global__ void __launch_bounds__(RoundtripWarpGeom<N>::NT, 4) roundtrip_warp_ke
         const bool two = 2 * pr + 1 < a.n_blocks;                         // an odd block count leaves the last pair with one block
         const int16_t *pa = a.in + s * a.in_pitch + 2 * pr * (long)N + t;
         const int16_t *pb = two ? pa + N : pa;
+        {   // pull the group's next block pair (4 N bytes) into L2 while this one is transformed: its 2 x 32 loads per thread then see
+            // L2 latency; costs no registers (the kernel sits at its 128-register cap) and no shared memory
+            dn.next();
+            if (item + wstride * (32 / G) < n_items) {
+                const char *nx = reinterpret_cast<const char *>(a.in + dn.q * a.in_pitch + 2 * dn.r * (long)N);
+                if (t * 128 < 4 * N) prefetch_l2_line(nx + t * 128);
+                if (G * 128 < 4 * N && (t + G) * 128 < 4 * N) prefetch_l2_line(nx + (t + G) * 128);
+            }
+        }
         cf reg[E];
 #pragma unroll
         for (int m = 0; m < E; ++m) reg[m] = cmake<float>(__int2float_rn((int)pa[G * m]), __int2float_rn((int)pb[G * m]));
