@@ -136,10 +136,9 @@ __global__ void __launch_bounds__(MfccGeom<NC>::NT, 2) mfcc_kernel(MfccArgs a) {
                 mbar_expect_tx(bar, bytes);
                 bulk_g2s(xs, src, bytes, bar);
             }
-        } else {
-            if (lane == 0) mbar_expect_tx(bar, (unsigned)(nf * W * 2));
-            __syncwarp();
-            if (lane < nf) bulk_g2s(xs + lane * SLOT, src + (long)lane * hop, (unsigned)(W * 2), bar);
+        } else if (lane == 0) {
+            mbar_expect_tx(bar, (unsigned)(nf * W * 2));
+            for (int i = 0; i < nf; ++i) bulk_g2s(xs + i * SLOT, src + (long)i * hop, (unsigned)(W * 2), bar);
         }
     };
     StridedDivmod dm((long)blockIdx.x, (long)gridDim.x, batches_per_utt), dn = dm;

@@ -262,6 +262,29 @@ def test_denoise_identity_property(be, dkernel):
     assert np.abs(got - expect).max() <= 1.0 + 1e-4 * 9000
 
 
+@pytest.mark.parametrize("mode", [SS, WIENER])
+def test_denoise_digital_silence_matches_the_oracle(be, dkernel, oracle, mode):
+    """All-zero frames: before the first noise publish the Wiener program computes 0/0 = NaN for every bin of such a frame and
+    writes (short)NaN = 0 for the two blocks the frame overlaps (WienerFilter_final.cpp:204-212); the SS program emits (-ns, 0) per
+    bin (atan2(0,0) = 0, appendix C-7).  Leading silence, silence between loud passages before any publish, and silence after the
+    noise spectrum exists must all come out like the restated program (which matches the compiled reference on these inputs)."""
+    p = be.L.denoise_params("bench", mode)
+    H, nb = p.hop, 90
+    rng = np.random.default_rng(5)
+    loud = rng.normal(0, 6000, nb * H).clip(-32768, 32767).astype(np.int16)
+    a = loud.copy(); a[:4 * H] = 0                       # leading digital silence, then loud audio (never classified as noise)
+    b = loud.copy(); b[5 * H:8 * H] = 0; b[20 * H:21 * H] = 0
+    c = synth.denoise_stream(41, nb * H).copy(); c[:3 * H] = 0; c[60 * H:66 * H] = 0   # speech + noise: silence after publishes
+    x = np.stack([a, b, c])
+    got = be.ctx.denoise(x, p)
+    for s in range(3):
+        ref = oracle.denoise(x[s], ODP.preset("bench", mode))
+        assert_i16_parity(got[s], ref.out, max_flip_frac=2e-3, what=f"silence case {s} mode {mode}")
+        zero_ref = np.abs(ref.out.reshape(-1, H)).max(axis=1) == 0
+        zero_got = np.abs(got[s].reshape(-1, H)).max(axis=1) == 0
+        assert np.array_equal(zero_ref, zero_got), f"all-zero output blocks differ in case {s}"
+
+
 @pytest.mark.parametrize("preset", ["bench", "ref"])
 @pytest.mark.parametrize("mode", [SS, WIENER])
 def test_denoise_kernels_bit_identical(be, monkeypatch, preset, mode):
@@ -445,6 +468,25 @@ def test_mfcc_generalised_framing_ragged(be, oracle, preset):
         feat = be.to_host(d_feat)
         for u in sorted({0, U // 2, U - 1}):
             assert_float_parity(feat[u], oracle.mfcc_frames(x[u], op), f"mfcc {preset} U={U}")
+    plan.close()
+
+
+@pytest.mark.parametrize("frame_len,hop", [(400, 512), (512, 1024), (240, 80), (512, 512)])
+def test_mfcc_sparse_and_dense_framings(be, oracle, frame_len, hop):
+    """Framings the presets do not cover: hops beyond the frame (every frame of a batch is staged by its own bulk copy instead of one
+    span copy), a dense hop (span copy, 32 frames share most of their samples) and abutting frames; frame counts around the 32-frame
+    batch of a CTA (31, 32, 33, 65) so that partial batches and the batch hand-over are hit."""
+    p = be.L.mfcc_params("bench"); p.frame_len = frame_len; p.hop = hop
+    op = OMP.preset("bench"); op.frame_len = frame_len; op.hop = hop
+    plan = be.ctx.mfcc_plan(p)
+    for U, nfr in ((2, 31), (1, 32), (3, 33), (2, 65)):
+        n = frame_len + (nfr - 1) * hop
+        x = np.stack([synth.mfcc_utterance(10 + u, n) for u in range(U)])
+        d_feat = be.zeros((U, nfr, p.n_cep), np.float32)
+        assert plan.run(be.to_dev(x), n, U, n, d_feat, nfr * p.n_cep) == nfr
+        feat = be.to_host(d_feat)
+        for u in range(U):
+            assert_float_parity(feat[u], oracle.mfcc_frames(x[u], op), f"mfcc frame {frame_len} hop {hop} U={U} frames={nfr}")
     plan.close()
 
 
