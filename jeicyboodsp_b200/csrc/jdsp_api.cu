@@ -166,7 +166,9 @@ static int launch_c2c_cluster2(jdsp_ctx *c, const cx<float> *in, cx<float> *out,
 // at N = 2^14 / 2^15 / 2^16 against 0.72 / 0.45 / 0.44 for the default plans.  One HBM round trip with whole sectors on both sides
 // (DRAM traffic 1.00x algorithmic), but with 16 warps per SM the load, exchange (two cluster barriers), three barrier-separated
 // passes and the transposing store of a 64 KB tile run too much one after the other: issue slots 24 % busy, long-scoreboard 2.6,
-// mio-throttle 2.6 and barrier 1.7 stall cycles per issue (ncu_fft_cluster16_summary.txt).
+// mio-throttle 2.6 and barrier 1.7 stall cycles per issue (ncu_fft_cluster16_summary.txt).  Twice the warps (512 threads x 16 points per
+// thread at 64 registers, two CTAs per SM) measured 0.36 at N = 2^15 against 0.39: more resident warps do not help, the cluster-wide
+// lockstep of load -> barrier -> exchange -> barrier -> transform does the damage.
 template <int N1, int N2, int C, bool INV>
 static int launch_c2c_cluster(jdsp_ctx *c, const cx<float> *in, cx<float> *out, long batch) {
     using Geo = FftClusterGeom<N1, N2, C>;
