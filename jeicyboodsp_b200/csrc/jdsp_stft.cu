@@ -227,6 +227,19 @@ template <int NC> static long denoise_stream_wave(jdsp_ctx *c) {
 // (measured, 512-pt preset on 148 SMs: 148 / 592 / 1184 / 2368 / 4096 streams -> tile 3.8x / 2.3x / 1.2x / 0.94x / 0.94x the
 // stream kernel's time): whole waves, and a remainder of at least 7/16 of a wave, go to the stream-group kernel; a smaller
 // remainder goes to the CTA-per-stream kernel.  JDSP_DENOISE_KERNEL=tile|stream forces one.
+// Measured and not kept (round 2, 4096 streams x 8 s; 4096 streams are 3.46 warps per scheduler and 3552 / 4096 / 4736 streams take
+// 1.68 / 2.15 / 2.16 ms): (a) 3552 streams on the stream-group kernel and the other 544 on the CTA-per-stream kernel at the same time on a
+// side stream (outputs identical): 2.20 ms.  (b) The call cut into 2..32 pieces per stream, carry state through the state arrays, pieces
+// handed to the warps through a ready queue in global memory (a warp that finishes piece k of a stream pushes piece k+1 and pops the oldest
+// ready piece, so faster warps take more pieces; outputs identical): 2.10-2.29 ms against 2.16 ms for one piece on the same build.  Per-item
+// timestamps show why it cannot pay: on every scheduler that holds four warps, three run at the pace of a three-warp scheduler and the
+// fourth at half of it (272 of the 2048 warps took 9 pieces while the others took 13-21), i.e. a scheduler is saturated by about 3.5 of
+// these warps and the work is throughput-bound per scheduler, not waiting for a balance.  Two pitfalls met on the way, both found with
+// timestamps and __activemask() inside the block loop: a wait loop or a queue operation executed by lane 0 alone at the end / start of
+// the item loop left lane 0 and lanes 1..31 scheduled as two separate halves for the whole next item (they met at every shuffle and parted
+// again: each block issued twice, 2x the time) -- warp-uniform polling and predicated single-lane atomics (no branch) cured it; and an
+// in-order hand-out (piece k+1 of a stream given to the next free warp whether or not piece k is done) kept 20 % of the warps waiting.
+// __nanosleep(t) does sleep for t (profiles/microbench/mb4.txt: 40 ns floor, then t rounded up to a power of two times 512 ns above 1 us).
 static int denoise_launch_slice(jdsp_ctx *c, jdsp_denoise_state *st, cudaStream_t stream, long stream0, long n, const int16_t *d_in,
                                 long in_pitch, long n_blocks, int16_t *d_out, long out_pitch, float *d_out_f32, long f32_pitch,
                                 uint8_t *d_vad) {
