@@ -174,6 +174,9 @@ template <int N> struct FftBigGeom {
     static constexpr size_t SMEM = (size_t)PADN * sizeof(cx<float>);
     static_assert(G <= 1024, "one CTA per transform");
 };
+// Resident CTAs per SM: 4 / 2 / 1 at 114 registers.  ptxas fits the kernel into 94 and 80 registers without spills, but 5 and 6 CTAs per SM
+// at N = 4096 measured 0.876 and 0.766 of the HBM peak against 0.921, and 3 at N = 8192 0.716 against 0.821 (round 2, same box, same minute):
+// more transforms in flight per SM thrash the exchange phases instead of overlapping them.
 template <int N, bool INV>
 __global__ void __launch_bounds__(FftBigGeom<N>::THREADS, N >= 16384 ? 1 : (N >= 8192 ? 2 : 4))
 fft_c2c_big_kernel(const cx<float> *__restrict__ in, cx<float> *__restrict__ out, long batch, const cx<float> *__restrict__ tw, float scale) {
