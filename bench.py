@@ -469,6 +469,21 @@ def cfg_mfcc(B: Bench):
     return res
 
 
+def _committed_traffic(S, n):
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        from capture_traffic import source_hash
+        doc = json.load(open(os.path.join(ROOT, "profiles", "round2", "traffic_denoise.json")))
+        if doc["kernel_sources_sha256"] != source_hash():
+            return None, "profiles/round2/traffic_denoise.json is stale (kernel sources changed since the capture)"
+        if doc["streams"] != S or doc["samples_per_stream"] != n:
+            return None, "profiles/round2/traffic_denoise.json was captured at another launch size"
+        return doc["dram_bytes_per_launch"], ("ncu dram__bytes_read.sum + dram__bytes_write.sum, mean of one SS and one Wiener launch at this size "
+                                              "(profiles/round2/traffic_denoise.json, kernel sources sha256 " + doc["kernel_sources_sha256"][:12] + ")")
+    except Exception as e:   # noqa: BLE001 - a missing capture is not an error of the run
+        return None, f"no committed capture ({type(e).__name__})"
+
+
 def cfg_sweep(B: Bench):
     """BASELINE configs[4]: batched complex64 FFT, N = 2^8 .. 2^16, 2^29 points = 4 GiB in + 4 GiB out per size."""
     import numpy as np
@@ -665,7 +680,9 @@ def main_gpu(args):
     roofline = _roof("jdsp::denoise_stream_kernel<256,MODE,16>", alg_bytes, avg_kernel_ms, FLOP_PER_SAMPLE["denoise"] * S * n,
                      "4 B/sample (int16 in + int16 out); one half warp per stream; the fp32 transforms and their shared-memory traffic, not HBM, bound it (DESIGN.md)")
     roofline["per_mode_ms"] = per_mode
-    roofline["traffic"] = None   # dram__bytes of one launch: see profiles/ (an ncu capture of this command); not re-measured inside the run
+    # dram__bytes of one launch cannot be measured inside an unprofiled run: it comes from a committed ncu capture of the same launch size
+    # (tools/capture_traffic.py) and is reported only while the kernel sources still hash to what was captured; otherwise null
+    roofline["traffic"], roofline["traffic_source"] = _committed_traffic(S, n)
 
     # ---- parity spot check on the very data that was timed (8 streams through the oracle) -------------------
     parity = None
