@@ -2,11 +2,12 @@
 input + 4 GiB): the L2-slice / HBM-channel hash makes some distances slower."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
-import torch, json
+import torch, json, time
 from jeicyboodsp_b200.binding import Context, Library
 PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
 L = Library(); ctx = Context(L, 0, stream=torch.cuda.current_stream().cuda_stream)
 total = 1 << 29
+IDLE = float(sys.argv[1]) if len(sys.argv) > 1 else 0.0
 maxpad = (512 << 20) // 8
 xy = torch.empty(2 * total + maxpad, dtype=torch.complex64, device="cuda")
 x = xy[:total]; torch.view_as_real(x).uniform_(-1, 1)
@@ -16,6 +17,7 @@ for pad_b in (0, 1 << 20, 0, 1 << 20, 0, 4096, 0):
     y = xy[total + pad_b // 8: 2 * total + pad_b // 8]
     fr = []
     for n in sizes:
+        if IDLE: torch.cuda.synchronize(); time.sleep(IDLE)
         for _ in range(3): ctx.fft_c2c_f32(x, y, n, total // n, True)
         ts = []
         for _ in range(7):
