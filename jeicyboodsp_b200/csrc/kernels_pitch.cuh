@@ -74,6 +74,14 @@ __global__ void __launch_bounds__(PitchGeom<NC>::NT) pitch_kernel(PitchArgs a) {
     const long n_items = a.n_streams * a.n_blocks;
     const int min_lag = a.min_lag;
 
+    // lags this thread may report: bit 2m / 2m+1 <-> lag 2(t + G m) / +1 in (min_lag, H)   (:100-108); built once, not per item
+    unsigned lagmask = 0;
+#pragma unroll
+    for (int m = 0; m < HM; ++m) {
+        const int l0 = 2 * (t + G * m);
+        if (l0 > min_lag) lagmask |= 1u << (2 * m);
+        if (l0 + 1 > min_lag) lagmask |= 1u << (2 * m + 1);
+    }
     StridedDivmod dm((long)blockIdx.x * Geo::WARPS + w, (long)gridDim.x * Geo::WARPS, a.n_blocks);
     for (long item = (long)blockIdx.x * Geo::WARPS + w; item < n_items; item += (long)gridDim.x * Geo::WARPS, dm.next()) {
         const long s = dm.q, b = dm.r;
@@ -127,9 +135,8 @@ __global__ void __launch_bounds__(PitchGeom<NC>::NT) pitch_kernel(PitchArgs a) {
         float vmax = -3.0e38f;
 #pragma unroll
         for (int m = 0; m < HM; ++m) {
-            const int l0 = 2 * (t + G * m);
-            if (l0 > min_lag) vmax = fmaxf(vmax, reg[m].x);
-            if (l0 + 1 > min_lag) vmax = fmaxf(vmax, reg[m].y);
+            if (lagmask & (1u << (2 * m))) vmax = fmaxf(vmax, reg[m].x);
+            if (lagmask & (2u << (2 * m))) vmax = fmaxf(vmax, reg[m].y);
         }
         vmax = warp_max_f32(vmax);
         // fp32 transform pair: measured |error| < 1e-6 r0; the band is 20x that plus one unit for tiny frames
@@ -137,10 +144,10 @@ __global__ void __launch_bounds__(PitchGeom<NC>::NT) pitch_kernel(PitchArgs a) {
         unsigned cand = 0;
 #pragma unroll
         for (int m = 0; m < HM; ++m) {
-            const int l0 = 2 * (t + G * m);
-            if (l0 > min_lag && reg[m].x >= thr) cand |= 1u << (2 * m);
-            if (l0 + 1 > min_lag && reg[m].y >= thr) cand |= 1u << (2 * m + 1);
+            if (reg[m].x >= thr) cand |= 1u << (2 * m);
+            if (reg[m].y >= thr) cand |= 2u << (2 * m);
         }
+        cand &= lagmask;
         // ---- decide on exact values, in the reference's scan order (descending lag, `>=`: :101-108) ------------------------
         __syncwarp();   // the staged frame is complete
         long long best = 0;
@@ -156,7 +163,7 @@ __global__ void __launch_bounds__(PitchGeom<NC>::NT) pitch_kernel(PitchArgs a) {
 #pragma unroll 8
             for (int j = 0; j < N / 32; ++j) {
                 const int k = t + 32 * j;
-                acc += (long long)((int)frame[k] * (int)frame[(k + top) & (N - 1)]);
+                acc += (long long)(int)frame[k] * (long long)(int)frame[(k + top) & (N - 1)];   // one 64-bit multiply-add (IMAD.WIDE)
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
