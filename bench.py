@@ -255,6 +255,10 @@ class Bench:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
+    def min_ranks_bool(self, ok: bool) -> bool:
+        """True only if `ok` holds on every rank."""
+        return self.max_ranks(0.0 if ok else 1.0) == 0.0
+
     def timed(self, fn, warm=3, reps=5, idle_s=0.0):
         """Mean device time of fn (CUDA events on the launching stream), max over ranks; inputs of every config exceed L2.
         idle_s > 0: the device is left idle that long before the warm-up launches (a kernel timed on its own, not inside a long run)."""
@@ -435,10 +439,36 @@ def cfg_mfcc(B: Bench):
                 hnd.wait()
         ms_over, _ = B.timed(overlapped, warm=2, reps=4)
         gathered_ok = bool(torch.equal(fullc[0, B.rank, : min(cu, U)], feat[: min(cu, U)]))
+        # the same result with NO collective: the scatter form of the kernel writes every feature row into every rank's copy of the matrix
+        # (peer memory over NVLink, jeicyboodsp_b200.sharding.PeerMatrix); a one-element all-reduce inside the timed region stands for "all
+        # ranks' rows have landed", which is what the all-gather's completion means
+        from jeicyboodsp_b200.sharding import PeerMatrix
+        serial()                                       # `full` = the NCCL result to compare with
+        pm = PeerMatrix(B.ctx, U_total, nf * 13)
+        dests = pm.dests(u_lo)
+        tiny = torch.zeros(1, dtype=torch.float32, device=dev)
+
+        def fused():
+            plan.run_scatter(x, n, U, n, dests, nf * 13)
+            dist.all_reduce(tiny)
+        ms_fused, _ = B.timed(fused, warm=2, reps=4)
+        torch.cuda.synchronize()
+        B.barrier()
+        M = pm.tensor().view(U_total, nf, 13)
+        fused_ok = True
+        for r in range(B.world):
+            lo, hi = shard_range(U_total, r, B.world)
+            fused_ok = fused_ok and bool(torch.equal(M[lo:hi], full[r * Umax: r * Umax + (hi - lo)]))
+        del M
+        pm.close()
         res["gather"] = {"collective": "NCCL all_gather_into_tensor of [utterances/N, 998, 13] f32 blocks -> one matrix on every rank",
                          "ms_kernel_only": ms, "ms_kernel_then_gather": ms_serial, "ms_chunked_overlap": ms_over, "chunks": NCH,
                          "bytes_received_per_rank": int((B.world - 1) * Umax * nf * 13 * 4), "own_block_intact": gathered_ok,
-                         "msamples_s_with_gather": U_total * n / ms_over / 1e3}
+                         "msamples_s_with_gather": U_total * n / ms_over / 1e3,
+                         "ms_fused_scatter": ms_fused, "fused_scatter_equals_nccl_result_on_every_rank": bool(B.min_ranks_bool(fused_ok)),
+                         "msamples_s_fused_scatter": U_total * n / ms_fused / 1e3,
+                         "fused_scatter": "jdsp_mfcc_frames_i16_scatter_dev: the kernel's feature rows written to all ranks' matrices through "
+                                          "CUDA-IPC peer mappings over NVLink (256-byte runs per warp store), then a 1-element all-reduce; no all-gather"}
         del pad, full, fullc, padc
     if B.world == 1 and not args.no_e2e:
         Ue = min(U, 4500 if not args.quick else 512)

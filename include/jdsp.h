@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define JDSP_ABI_VERSION 4
+#define JDSP_ABI_VERSION 5
 
 #define JDSP_OK 0
 #define JDSP_ERR_INVALID (-1)     /* bad argument */
@@ -64,6 +64,15 @@ int jdsp_host_alloc(jdsp_ctx *ctx, void **h_ptr, size_t bytes); /* pinned */
 int jdsp_host_free(jdsp_ctx *ctx, void *h_ptr);
 int jdsp_memcpy_h2d(jdsp_ctx *ctx, void *d_dst, const void *h_src, size_t bytes); /* async on the ctx stream */
 int jdsp_memcpy_d2h(jdsp_ctx *ctx, void *h_dst, const void *d_src, size_t bytes); /* async on the ctx stream */
+
+/* Peer memory (no reference counterpart: the reference is one process per file, MFCCFeatureExtraction_auto_version1.cpp:68-101).
+ * One process per GPU: a jdsp_malloc'ed buffer is exported as a 64-byte handle, sent to the processes that drive the other
+ * GPUs of the box by any means, and opened there; the address it maps to can be handed to the scatter form below, whose
+ * kernel then writes into the owner's memory over NVLink.  Close before the owner frees. */
+typedef struct { unsigned char bytes[64]; } jdsp_peer_handle;
+int jdsp_peer_export(jdsp_ctx *ctx, void *d_ptr, jdsp_peer_handle *handle);
+int jdsp_peer_open(jdsp_ctx *ctx, const jdsp_peer_handle *handle, void **d_ptr);
+int jdsp_peer_close(jdsp_ctx *ctx, void *d_ptr);
 
 /* ---- K1: FFT -------------------------------------------------------------------------------------- */
 /*
@@ -280,6 +289,13 @@ int jdsp_mfcc_plan_tables(jdsp_mfcc_plan *plan, double *weight, int32_t *chan);
  *   *n_frames (nullable, host) = (n_samples - frame_len)/hop + 1. */
 int jdsp_mfcc_frames_i16_dev(jdsp_ctx *ctx, jdsp_mfcc_plan *plan, const int16_t *d_in, long in_pitch, long n_utts,
                              long n_samples, float *d_feat, long feat_pitch, long *n_frames);
+/* Scatter form for a run sharded by utterance over the GPUs of one box (the optional gather of the per-GPU feature
+ * blocks into one matrix, MFCCFeatureExtraction_auto_version1.cpp:68-101 being the file-per-process model it replaces): the
+ * kernel writes every feature row to n_dest (1..8) matrices at once -- this GPU's own and, through jdsp_peer_open'ed
+ * addresses, its peers' -- so that when all ranks' kernels have finished every GPU holds the whole matrix and no collective
+ * follows.  d_dest[i] = where utterance 0 of THIS call lies inside matrix i; all matrices share feat_pitch. */
+int jdsp_mfcc_frames_i16_scatter_dev(jdsp_ctx *ctx, jdsp_mfcc_plan *plan, const int16_t *d_in, long in_pitch, long n_utts,
+                                     long n_samples, int n_dest, float *const *d_dest, long feat_pitch, long *n_frames);
 /* The same on HOST buffers (in [utt][n_samples], feat [utt][n_frames][n_cep]), pipelined over chunks of utterances. */
 int jdsp_mfcc_frames_i16(jdsp_ctx *ctx, jdsp_mfcc_plan *plan, const int16_t *in, long in_pitch, long n_utts, long n_samples,
                          float *feat, long feat_pitch, long *n_frames);

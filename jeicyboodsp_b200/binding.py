@@ -81,7 +81,8 @@ ABI_SYMBOLS = [
     "jdsp_fastconv_params_preset", "jdsp_fastconv_state_create", "jdsp_fastconv_state_reset",
     "jdsp_fastconv_state_destroy", "jdsp_fastconv_i16_dev", "jdsp_fastconv_mix_i16_dev", "jdsp_fastconv_i16",
     "jdsp_mfcc_params_preset", "jdsp_mfcc_plan_create", "jdsp_mfcc_plan_destroy", "jdsp_mfcc_plan_tables",
-    "jdsp_mfcc_frames_i16_dev", "jdsp_mfcc_program_i16",
+    "jdsp_mfcc_frames_i16_dev", "jdsp_mfcc_frames_i16_scatter_dev", "jdsp_mfcc_program_i16",
+    "jdsp_peer_export", "jdsp_peer_open", "jdsp_peer_close",
     "jdsp_pitch_params_preset", "jdsp_pitch_state_create", "jdsp_pitch_state_reset", "jdsp_pitch_state_destroy",
     "jdsp_pitch_i16_dev", "jdsp_pitch_i16",
     "jdsp_mvdr_params_preset", "jdsp_mvdr_state_create", "jdsp_mvdr_state_reset", "jdsp_mvdr_state_destroy",
@@ -168,6 +169,29 @@ class Context:
 
     def cuda_stream(self) -> int:
         return int(self.lib.jdsp_cuda_stream(self.h) or 0)
+
+    # ---- raw device memory and peer mapping (CUDA IPC) for the scatter form of the MFCC kernel ----------------
+    def malloc(self, nbytes: int) -> int:
+        p = C.c_void_p(0)
+        self.L.check(self.lib.jdsp_malloc(self.h, C.byref(p), C.c_size_t(nbytes)))
+        return int(p.value)
+
+    def free(self, addr: int) -> None:
+        self.L.check(self.lib.jdsp_free(self.h, C.c_void_p(addr)))
+
+    def peer_export(self, addr: int) -> bytes:
+        h = (C.c_ubyte * 64)()
+        self.L.check(self.lib.jdsp_peer_export(self.h, C.c_void_p(addr), C.byref(h)))
+        return bytes(h)
+
+    def peer_open(self, handle: bytes) -> int:
+        h = (C.c_ubyte * 64).from_buffer_copy(handle)
+        p = C.c_void_p(0)
+        self.L.check(self.lib.jdsp_peer_open(self.h, C.byref(h), C.byref(p)))
+        return int(p.value)
+
+    def peer_close(self, addr: int) -> None:
+        self.L.check(self.lib.jdsp_peer_close(self.h, C.c_void_p(addr)))
 
     def kernel_launches(self) -> int:
         n = C.c_uint64(0)
@@ -461,4 +485,14 @@ class MfccPlan:
         self.ctx.L.check(self.ctx.lib.jdsp_mfcc_frames_i16_dev(self.ctx.h, self.h, _ptr(d_in), C.c_long(in_pitch),
                                                                C.c_long(n_utts), C.c_long(n_samples), _ptr(d_feat),
                                                                C.c_long(feat_pitch), C.byref(got)))
+        return got.value
+
+    def run_scatter(self, d_in, in_pitch, n_utts, n_samples, dests, feat_pitch) -> int:
+        """Scatter form: every feature row goes to all `dests` (device addresses or tensors: where utterance 0 of this call lies inside
+        each destination matrix -- this GPU's and, through Context.peer_open, its peers')."""
+        got = C.c_long(0)
+        arr = (C.c_void_p * len(dests))(*[_ptr(d) for d in dests])
+        self.ctx.L.check(self.ctx.lib.jdsp_mfcc_frames_i16_scatter_dev(self.ctx.h, self.h, _ptr(d_in), C.c_long(in_pitch), C.c_long(n_utts),
+                                                                       C.c_long(n_samples), C.c_int(len(dests)), arr, C.c_long(feat_pitch),
+                                                                       C.byref(got)))
         return got.value

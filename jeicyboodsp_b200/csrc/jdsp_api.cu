@@ -65,6 +65,46 @@ int jdsp_kernel_launches(jdsp_ctx *c, uint64_t *count) { REQUIRE(c && count, "nu
 
 int jdsp_malloc(jdsp_ctx *c, void **d, size_t bytes) { REQUIRE(c && d, "null argument"); CU(cudaSetDevice(c->device)); CU(cudaMalloc(d, bytes)); return JDSP_OK; }
 int jdsp_free(jdsp_ctx *c, void *d) { REQUIRE(c, "ctx is null"); CU(cudaFree(d)); return JDSP_OK; }
+// Peer memory: a buffer one process allocates and the processes that drive the other GPUs of the box map into their own address space
+// (CUDA IPC); a kernel then stores into it over NVLink like into any other global address.  jdsp_malloc'ed (cudaMalloc) buffers only.
+int jdsp_peer_export(jdsp_ctx *c, void *d, jdsp_peer_handle *h) {
+    REQUIRE(c && d && h, "null argument");
+#ifndef JDSP_EMUL
+    static_assert(sizeof(cudaIpcMemHandle_t) == sizeof(jdsp_peer_handle), "handle size");
+#endif
+#ifdef JDSP_EMUL
+    return fail(JDSP_ERR_UNSUPPORTED, "peer memory needs CUDA devices");
+#else
+    CU(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t ih;
+    CU(cudaIpcGetMemHandle(&ih, d));
+    memcpy(h, &ih, sizeof(ih));
+    return JDSP_OK;
+#endif
+}
+int jdsp_peer_open(jdsp_ctx *c, const jdsp_peer_handle *h, void **d) {
+    REQUIRE(c && h && d, "null argument");
+#ifdef JDSP_EMUL
+    return fail(JDSP_ERR_UNSUPPORTED, "peer memory needs CUDA devices");
+#else
+    CU(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t ih;
+    memcpy(&ih, h, sizeof(ih));
+    CU(cudaIpcOpenMemHandle(d, ih, cudaIpcMemLazyEnablePeerAccess));
+    return JDSP_OK;
+#endif
+}
+int jdsp_peer_close(jdsp_ctx *c, void *d) {
+    REQUIRE(c, "ctx is null");
+    if (!d) return JDSP_OK;
+#ifdef JDSP_EMUL
+    return fail(JDSP_ERR_UNSUPPORTED, "peer memory needs CUDA devices");
+#else
+    CU(cudaSetDevice(c->device));
+    CU(cudaIpcCloseMemHandle(d));
+    return JDSP_OK;
+#endif
+}
 int jdsp_host_alloc(jdsp_ctx *c, void **h, size_t bytes) { REQUIRE(c && h, "null argument"); CU(cudaMallocHost(h, bytes)); return JDSP_OK; }
 int jdsp_host_free(jdsp_ctx *c, void *h) { REQUIRE(c, "ctx is null"); CU(cudaFreeHost(h)); return JDSP_OK; }
 int jdsp_memcpy_h2d(jdsp_ctx *c, void *d, const void *h, size_t bytes) { REQUIRE(c, "ctx is null"); CU(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c->stream)); return JDSP_OK; }

@@ -345,15 +345,17 @@ template <int NC, int MU> static int launch_mfcc(jdsp_ctx *c, const MfccArgs &a)
     return launch_check(c);
 }
 
-extern "C" {
-int jdsp_mfcc_frames_i16_dev(jdsp_ctx *c, jdsp_mfcc_plan *pl, const int16_t *d_in, long in_pitch, long n_utts, long n_samples,
-                             float *d_feat, long feat_pitch, long *n_frames) {
+// d_feat (one matrix) or n_dest > 0 destinations (scatter form: this GPU's matrix and its peers')
+static int mfcc_frames_dev(jdsp_ctx *c, jdsp_mfcc_plan *pl, const int16_t *d_in, long in_pitch, long n_utts, long n_samples,
+                           float *d_feat, int n_dest, float *const *d_dest, long feat_pitch, long *n_frames) {
     REQUIRE(c && pl && d_in, "null argument");
     const jdsp_mfcc_params &p = pl->p;
     const long nf = n_samples >= p.frame_len ? (n_samples - p.frame_len) / p.hop + 1 : 0;
     if (n_frames) *n_frames = nf;
     if (nf == 0 || n_utts == 0) return JDSP_OK;
-    REQUIRE(d_feat, "d_feat is null");
+    REQUIRE(n_dest > 0 || d_feat, "d_feat is null");
+    REQUIRE(n_dest >= 0 && n_dest <= MFCC_MAX_DEST, "at most 8 destinations");
+    for (int i = 0; i < n_dest; ++i) REQUIRE(d_dest && d_dest[i], "null destination");
     REQUIRE(in_pitch % 8 == 0 && (((uintptr_t)d_in) & 15) == 0, "utterance rows must be 16-byte aligned (in_pitch % 8 == 0)");
     REQUIRE(feat_pitch >= nf * p.n_cep, "feat_pitch too small");
     CU(cudaSetDevice(c->device));
@@ -364,6 +366,8 @@ int jdsp_mfcc_frames_i16_dev(jdsp_ctx *c, jdsp_mfcc_plan *pl, const int16_t *d_i
     MfccArgs a;
     a.in = d_in; a.in_pitch = in_pitch; a.n_utts = n_utts; a.n_frames = nf;
     a.feat = d_feat; a.feat_pitch = feat_pitch; a.win_half = pl->d_win_half; a.tw = (const cf *)tw; a.twr = (const float2 *)twr;
+    a.n_dest = n_dest;
+    for (int i = 0; i < MFCC_MAX_DEST; ++i) a.dest[i] = i < n_dest ? d_dest[i] : nullptr;
     a.tri = pl->d_tri; a.chan_tab = (const int2 *)pl->d_chan_tab; a.grp_len = pl->d_grp_len; a.dct = pl->d_dct;
     a.frame_len = p.frame_len; a.hop = p.hop; a.n_mel = p.n_mel; a.n_cep = p.n_cep; a.preemph = (float)p.preemph;
     a.n_tri = pl->n_tri;
@@ -374,6 +378,17 @@ int jdsp_mfcc_frames_i16_dev(jdsp_ctx *c, jdsp_mfcc_plan *pl, const int16_t *d_i
     // samples (the bench preset's 400 of 512)
     if (NC == 256) return p.frame_len <= 13 * 32 ? launch_mfcc<256, 13>(c, a) : launch_mfcc<256, 16>(c, a);
     return launch_mfcc<512, 16>(c, a);
+}
+
+extern "C" {
+int jdsp_mfcc_frames_i16_dev(jdsp_ctx *c, jdsp_mfcc_plan *pl, const int16_t *d_in, long in_pitch, long n_utts, long n_samples,
+                             float *d_feat, long feat_pitch, long *n_frames) {
+    return mfcc_frames_dev(c, pl, d_in, in_pitch, n_utts, n_samples, d_feat, 0, nullptr, feat_pitch, n_frames);
+}
+int jdsp_mfcc_frames_i16_scatter_dev(jdsp_ctx *c, jdsp_mfcc_plan *pl, const int16_t *d_in, long in_pitch, long n_utts, long n_samples,
+                                     int n_dest, float *const *d_dest, long feat_pitch, long *n_frames) {
+    REQUIRE(n_dest >= 1, "the scatter form needs at least one destination");
+    return mfcc_frames_dev(c, pl, d_in, in_pitch, n_utts, n_samples, nullptr, n_dest, d_dest, feat_pitch, n_frames);
 }
 
 int jdsp_mfcc_frames_i16(jdsp_ctx *c, jdsp_mfcc_plan *pl, const int16_t *in, long in_pitch, long n_utts, long n_samples, float *feat,

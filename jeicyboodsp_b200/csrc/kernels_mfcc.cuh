@@ -37,7 +37,13 @@ struct MfccArgs {
     int frame_len, hop, n_mel, n_cep, n_tri;
     int slot;                              // samples between the staged starts of consecutive frames: hop (one span copy) or frame_len + 8
     float preemph;
+    // Scatter form (n_dest > 0; `feat` unused): the feature rows of every batch go to n_dest matrices at once -- this GPU's own and its
+    // peers' over NVLink (peer memory mapped by CUDA IPC) -- so that a sharded run leaves the WHOLE matrix on every GPU without a
+    // collective after the kernel.  dest[d] points at utterance 0 of THIS launch inside matrix d; all share feat_pitch.
+    float *dest[8];
+    int n_dest;
 };
+constexpr int MFCC_MAX_DEST = 8;
 
 template <int NC>
 struct MfccGeom {
@@ -59,6 +65,7 @@ struct MfccGeom {
         const int cpad = (n_mel + 3) & ~3;
         size_t s = OFF_VAR + (size_t)n_mel * MP * 4 + (size_t)n_mel * 16 * 4 + (size_t)cpad * 8 + (size_t)(cpad / 4) * 4 + (size_t)n_tri * 4;
         s = (s + 15) & ~(size_t)15;
+        s += (size_t)FB * MAXCEP * 4;                     // the batch's feature rows, staged for the scatter form
         return s + ((size_t)(FB - 1) * slot + N) * 2;
     }
     static_assert(G == 16 || G == 32, "a frame group is a half warp or a warp");
@@ -95,8 +102,10 @@ __global__ void __launch_bounds__(MfccGeom<NC>::NT, 2) mfcc_kernel(MfccArgs a) {
     int2 *chtab = reinterpret_cast<int2 *>(dct + C * 16);
     int *glen = reinterpret_cast<int *>(chtab + CPAD);
     float *tri = reinterpret_cast<float *>(glen + CPAD / 4);
-    const size_t off_pcm = (Geo::OFF_VAR + (size_t)C * MP * 4 + (size_t)C * 16 * 4 + (size_t)CPAD * 8 + (size_t)(CPAD / 4) * 4 + (size_t)NTRI * 4 + 15) & ~(size_t)15;
-    int16_t *xs = reinterpret_cast<int16_t *>(smem_raw + off_pcm);
+    const size_t off_stage = (Geo::OFF_VAR + (size_t)C * MP * 4 + (size_t)C * 16 * 4 + (size_t)CPAD * 8 + (size_t)(CPAD / 4) * 4 + (size_t)NTRI * 4 + 15) & ~(size_t)15;
+    float *stage = reinterpret_cast<float *>(smem_raw + off_stage);        // [frame of the batch][n_cep]: the batch's rows as they lie in the matrix
+    int16_t *xs = reinterpret_cast<int16_t *>(smem_raw + off_stage + (size_t)FB * Geo::MAXCEP * 4);
+    const int n_dest = a.n_dest;
 
     // ---- tables (once per CTA) -----------------------------------------------------------------------------------
     for (int i = tid; i < Geo::NTW; i += NT) tw[i] = a.tw[i];
@@ -235,11 +244,36 @@ __global__ void __launch_bounds__(MfccGeom<NC>::NT, 2) mfcc_kernel(MfccArgs a) {
                 acc[0] = fmaf(d.x, lm, acc[0]); acc[1] = fmaf(d.y, lm, acc[1]);
                 acc[2] = fmaf(d.z, lm, acc[2]); acc[3] = fmaf(d.w, lm, acc[3]);
             }
-            if (lane < nfb) {
-                float *dst = a.feat + dm.q * feat_pitch + (dm.r * FB + lane) * NCEP + warp * CPW;
+            if (n_dest == 0) {
+                if (lane < nfb) {
+                    float *dst = a.feat + dm.q * feat_pitch + (dm.r * FB + lane) * NCEP + warp * CPW;
+#pragma unroll
+                    for (int i = 0; i < CPW; ++i)
+                        if (warp * CPW + i < NCEP) dst[i] = acc[i];
+                }
+            } else {
 #pragma unroll
                 for (int i = 0; i < CPW; ++i)
-                    if (warp * CPW + i < NCEP) dst[i] = acc[i];
+                    if (warp * CPW + i < NCEP) stage[lane * NCEP + warp * CPW + i] = acc[i];
+            }
+        }
+        if (n_dest > 0) {
+            // ---- scatter: the batch's rows are ONE contiguous run of nfb * n_cep floats in every destination matrix; warp d writes the run
+            // to destination d with whole-warp 8-byte stores (256 contiguous bytes per instruction: full sectors locally, full NVLink
+            // write packets to a peer), straight from the staged copy.  The next batch's B2 writes `stage` two barriers from here.
+            __syncthreads();
+            const long off = dm.q * feat_pitch + (long)dm.r * FB * NCEP;
+            const int nfl = nfb * NCEP;
+            for (int d = warp; d < n_dest; d += NW) {
+                float *dp = a.dest[d] + off;
+                if ((reinterpret_cast<uintptr_t>(dp) & 7) == 0) {
+                    float2 *dp2 = reinterpret_cast<float2 *>(dp);
+                    const float2 *sp2 = reinterpret_cast<const float2 *>(stage);
+                    for (int i = lane; i < nfl / 2; i += 32) dp2[i] = sp2[i];
+                    if ((nfl & 1) && lane == 0) dp[nfl - 1] = stage[nfl - 1];
+                } else {
+                    for (int i = lane; i < nfl; i += 32) dp[i] = stage[i];
+                }
             }
         }
         // no barrier here: the next batch's Phase A touches the exchange buffers and mag, which B2 does not read, and its B1 rewrites

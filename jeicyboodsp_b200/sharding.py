@@ -1,7 +1,8 @@
 """Multi-GPU plumbing.  Streams / sources / utterances are independent, so the hot path
 shards with NO data-path collective: rank r owns a contiguous slice of the leading index and its own
 per-stream state.  The only collective anywhere is the optional all-gather of per-GPU MFCC feature blocks
-when a caller wants a single feature matrix (NCCL over NVLink on GPUs, gloo in the CPU tests)."""
+when a caller wants a single feature matrix (NCCL over NVLink on GPUs, gloo in the CPU tests) -- or, without any
+collective, the scatter form of the MFCC kernel writing straight into every GPU's copy of the matrix (PeerMatrix)."""
 from __future__ import annotations
 
 
@@ -40,3 +41,53 @@ def allgather_features(local, n_units_total: int):
     dist.all_gather_into_tensor(out, pad)
     parts = [out[r * biggest: r * biggest + (e - b)] for r, (b, e) in enumerate(sizes)]
     return torch.cat(parts, dim=0)
+
+
+class PeerMatrix:
+    """One [n_units_total, row_floats] float32 matrix per rank, every rank's copy mapped into all the other ranks of the box
+    (CUDA IPC over NVLink).  `dests(unit0)` are the addresses at which unit `unit0` lies in each copy: handed to
+    MfccPlan.run_scatter, every rank's kernel writes its own block into ALL copies, so that once all kernels have finished
+    every rank holds the whole matrix -- the fused replacement of kernel + all-gather.  Creation and close() are collective
+    calls (every rank of the default process group)."""
+
+    def __init__(self, ctx, n_units_total: int, row_floats: int):
+        import torch.distributed as dist
+        self.ctx, self.n_units, self.row = ctx, n_units_total, row_floats
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.nbytes = n_units_total * row_floats * 4
+        self.local = ctx.malloc(self.nbytes)
+        handles = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(handles, ctx.peer_export(self.local))
+        self.addrs = [self.local if r == self.rank else ctx.peer_open(handles[r]) for r in range(self.world)]
+
+    def dests(self, unit0: int) -> list[int]:
+        off = unit0 * self.row * 4
+        # own copy first: its stores stay on this GPU and do not queue behind the NVLink ones
+        order = [self.rank] + [r for r in range(self.world) if r != self.rank]
+        return [self.addrs[r] + off for r in order]
+
+    def tensor(self):
+        """This rank's copy as a torch tensor [n_units_total, row_floats] (no copy)."""
+        import torch
+
+        class _Raw:
+            pass
+        raw = _Raw()
+        raw.__cuda_array_interface__ = {"shape": (self.n_units, self.row), "typestr": "<f4", "data": (self.local, False), "version": 3, "strides": None}
+        return torch.as_tensor(raw, device=f"cuda:{torch.cuda.current_device()}")
+
+    def close(self) -> None:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()           # nobody unmaps or frees while a peer may still be writing
+        for r, a in enumerate(self.addrs):
+            if r != self.rank:
+                self.ctx.peer_close(a)
+        if self.world > 1:
+            dist.barrier()           # every mapping of this rank's copy is gone before it is freed
+        self.ctx.free(self.local)
+        self.addrs, self.local = [], 0

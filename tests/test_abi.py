@@ -30,7 +30,7 @@ def test_exports_every_declared_symbol(lib):
     assert sorted(ABI_SYMBOLS) == declared, "binding.ABI_SYMBOLS must list exactly what the header declares"
     for name in declared:
         assert hasattr(lib.lib, name), f"libjdsp.so does not export {name}"
-    assert lib.lib.jdsp_abi_version() == 4
+    assert lib.lib.jdsp_abi_version() == 5
 
 
 def test_struct_layouts_match_header(lib):

@@ -506,6 +506,33 @@ def test_mfcc_bench_framing(be, oracle):
     plan.close()
 
 
+@pytest.mark.parametrize("pad", [0, 1, 3])
+def test_mfcc_scatter_form_equals_plain(be, pad):
+    """The scatter form (every feature row written to several matrices at once: the fused replacement of kernel + all-gather on a
+    sharded run) must put bit for bit what the plain form returns at the right place of EVERY destination -- for a dense and for padded
+    utterance pitches (8-byte and 4-byte aligned runs), with a ragged last batch of frames, and must not touch anything else."""
+    p = be.L.mfcc_params("bench")
+    n = 8000 if be.name == "emul" else 53000          # 48 / 329 frames: not a multiple of the 32-frame batch
+    U, total_u, u0 = 3, 7, 2                          # this "rank" owns utterances 2..4 of a 7-utterance matrix
+    x = np.stack([synth.mfcc_utterance(20 + u, n) for u in range(U)])
+    plan = be.ctx.mfcc_plan(p)
+    nf = plan.n_frames(n)
+    pitch = nf * 13 + pad
+    d_in = be.to_dev(x)
+    d_plain = be.zeros((U, pitch), np.float32)
+    assert plan.run(d_in, n, U, n, d_plain, pitch) == nf
+    plain = be.to_host(d_plain)
+    mats = [be.zeros((total_u, pitch), np.float32) for _ in range(3)]
+    for m in mats:
+        m[...] = -7.0
+    assert plan.run_scatter(d_in, n, U, n, [m[u0:] for m in mats], pitch) == nf
+    for m in mats:
+        got = be.to_host(m)
+        assert np.array_equal(got[u0:u0 + U, : nf * 13], plain[:, : nf * 13])
+        assert np.all(got[:u0] == -7.0) and np.all(got[u0 + U:] == -7.0) and np.all(got[:, nf * 13:] == -7.0)
+    plan.close()
+
+
 # ---- host-buffer forms: chunked copy / compute pipelines must return exactly what one device-resident call returns ----------
 def test_host_forms_chunked_equal_resident(be, oracle, monkeypatch):
     import ctypes as C
