@@ -329,9 +329,9 @@ int jdsp_mfcc_plan_tables(jdsp_mfcc_plan *pl, double *weight, int32_t *chan) {
 }
 }  // extern "C"
 
-template <int NC, int MU> static int launch_mfcc(jdsp_ctx *c, const MfccArgs &a) {
+template <int NC, int MU, bool SCATTER> static int launch_mfcc_v(jdsp_ctx *c, const MfccArgs &a) {
     using Geo = MfccGeom<NC>;
-    auto kfn = mfcc_kernel<NC, MU>;
+    auto kfn = mfcc_kernel<NC, MU, SCATTER>;
     const size_t smem = Geo::smem(a.n_mel, a.n_tri, a.slot);
     if (smem > 227 * 1024) return fail(JDSP_ERR_UNSUPPORTED, "MFCC: frame hop / channel count too large for the kernel's shared-memory layout");
     TRY(opt_in_smem(kfn, smem));
@@ -343,6 +343,10 @@ template <int NC, int MU> static int launch_mfcc(jdsp_ctx *c, const MfccArgs &a)
     const long batches = a.n_utts * ((a.n_frames + Geo::FB - 1) / Geo::FB);
     JDSP_LAUNCH_PTR(kfn, dim3(grid_for(c, batches, per_sm)), dim3(Geo::NT), smem, c->stream, a);
     return launch_check(c);
+}
+
+template <int NC, int MU> static int launch_mfcc(jdsp_ctx *c, const MfccArgs &a) {
+    return a.n_dest > 0 ? launch_mfcc_v<NC, MU, true>(c, a) : launch_mfcc_v<NC, MU, false>(c, a);
 }
 
 // d_feat (one matrix) or n_dest > 0 destinations (scatter form: this GPU's matrix and its peers')
