@@ -461,12 +461,39 @@ def cfg_mfcc(B: Bench):
             fused_ok = fused_ok and bool(torch.equal(M[lo:hi], full[r * Umax: r * Umax + (hi - lo)]))
         del M
         pm.close()
+        # ... and through ONE NVLink multicast address: each row leaves the GPU once, the NVSwitch replicates it into every copy
+        mc = {"available": False}
+        try:
+            from jeicyboodsp_b200.sharding import MulticastMatrix
+            mm = MulticastMatrix(U_total, nf * 13, dev)
+            if mm.available():
+                mcd = mm.dest(u_lo)
+
+                def fused_mc():
+                    plan.run_multicast(x, n, U, n, mcd, nf * 13)
+                    dist.all_reduce(tiny)
+                ms_mc, _ = B.timed(fused_mc, warm=2, reps=4)
+                torch.cuda.synchronize()
+                B.barrier()
+                Mm = mm.tensor().view(U_total, nf, 13)
+                mc_ok = True
+                for r in range(B.world):
+                    lo, hi = shard_range(U_total, r, B.world)
+                    mc_ok = mc_ok and bool(torch.equal(Mm[lo:hi], full[r * Umax: r * Umax + (hi - lo)]))
+                mc = {"available": True, "ms": ms_mc, "equals_nccl_result_on_every_rank": bool(B.min_ranks_bool(mc_ok)),
+                      "msamples_s": U_total * n / ms_mc / 1e3,
+                      "how": "jdsp_mfcc_frames_i16_multicast_dev: multimem.st to the multicast address of torch symmetric memory (NVSwitch replicates "
+                             "each 256-byte warp store into all ranks' matrices), then a 1-element all-reduce"}
+                del Mm
+            del mm
+        except Exception as e:   # noqa: BLE001 - no symmetric memory / multicast on this platform: the unicast scatter above stands
+            mc = {"available": False, "why": f"{type(e).__name__}: {e}"[:200]}
         res["gather"] = {"collective": "NCCL all_gather_into_tensor of [utterances/N, 998, 13] f32 blocks -> one matrix on every rank",
                          "ms_kernel_only": ms, "ms_kernel_then_gather": ms_serial, "ms_chunked_overlap": ms_over, "chunks": NCH,
                          "bytes_received_per_rank": int((B.world - 1) * Umax * nf * 13 * 4), "own_block_intact": gathered_ok,
                          "msamples_s_with_gather": U_total * n / ms_over / 1e3,
                          "ms_fused_scatter": ms_fused, "fused_scatter_equals_nccl_result_on_every_rank": bool(B.min_ranks_bool(fused_ok)),
-                         "msamples_s_fused_scatter": U_total * n / ms_fused / 1e3,
+                         "msamples_s_fused_scatter": U_total * n / ms_fused / 1e3, "fused_multicast": mc,
                          "fused_scatter": "jdsp_mfcc_frames_i16_scatter_dev: the kernel's feature rows written to all ranks' matrices through "
                                           "CUDA-IPC peer mappings over NVLink (256-byte runs per warp store), then a 1-element all-reduce; no all-gather"}
         del pad, full, fullc, padc

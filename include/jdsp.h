@@ -296,6 +296,12 @@ int jdsp_mfcc_frames_i16_dev(jdsp_ctx *ctx, jdsp_mfcc_plan *plan, const int16_t 
  * follows.  d_dest[i] = where utterance 0 of THIS call lies inside matrix i; all matrices share feat_pitch. */
 int jdsp_mfcc_frames_i16_scatter_dev(jdsp_ctx *ctx, jdsp_mfcc_plan *plan, const int16_t *d_in, long in_pitch, long n_utts,
                                      long n_samples, int n_dest, float *const *d_dest, long feat_pitch, long *n_frames);
+/* The scatter form through ONE NVLink multicast address: d_mc_dest = where utterance 0 of this call lies in the multicast
+ * mapping of the matrix (an NVSwitch multicast object bound to the same offset of every GPU's copy, e.g. the multicast_ptr of
+ * torch's symmetric memory); every row leaves this GPU once (multimem.st) and the switch writes it into all copies, this
+ * GPU's included. */
+int jdsp_mfcc_frames_i16_multicast_dev(jdsp_ctx *ctx, jdsp_mfcc_plan *plan, const int16_t *d_in, long in_pitch, long n_utts,
+                                       long n_samples, float *d_mc_dest, long feat_pitch, long *n_frames);
 /* The same on HOST buffers (in [utt][n_samples], feat [utt][n_frames][n_cep]), pipelined over chunks of utterances. */
 int jdsp_mfcc_frames_i16(jdsp_ctx *ctx, jdsp_mfcc_plan *plan, const int16_t *in, long in_pitch, long n_utts, long n_samples,
                          float *feat, long feat_pitch, long *n_frames);

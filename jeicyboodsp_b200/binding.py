@@ -81,7 +81,7 @@ ABI_SYMBOLS = [
     "jdsp_fastconv_params_preset", "jdsp_fastconv_state_create", "jdsp_fastconv_state_reset",
     "jdsp_fastconv_state_destroy", "jdsp_fastconv_i16_dev", "jdsp_fastconv_mix_i16_dev", "jdsp_fastconv_i16",
     "jdsp_mfcc_params_preset", "jdsp_mfcc_plan_create", "jdsp_mfcc_plan_destroy", "jdsp_mfcc_plan_tables",
-    "jdsp_mfcc_frames_i16_dev", "jdsp_mfcc_frames_i16_scatter_dev", "jdsp_mfcc_program_i16",
+    "jdsp_mfcc_frames_i16_dev", "jdsp_mfcc_frames_i16_scatter_dev", "jdsp_mfcc_frames_i16_multicast_dev", "jdsp_mfcc_program_i16",
     "jdsp_peer_export", "jdsp_peer_open", "jdsp_peer_close",
     "jdsp_pitch_params_preset", "jdsp_pitch_state_create", "jdsp_pitch_state_reset", "jdsp_pitch_state_destroy",
     "jdsp_pitch_i16_dev", "jdsp_pitch_i16",
@@ -485,6 +485,13 @@ class MfccPlan:
         self.ctx.L.check(self.ctx.lib.jdsp_mfcc_frames_i16_dev(self.ctx.h, self.h, _ptr(d_in), C.c_long(in_pitch),
                                                                C.c_long(n_utts), C.c_long(n_samples), _ptr(d_feat),
                                                                C.c_long(feat_pitch), C.byref(got)))
+        return got.value
+
+    def run_multicast(self, d_in, in_pitch, n_utts, n_samples, mc_dest, feat_pitch) -> int:
+        """Scatter form through one NVLink multicast address (where utterance 0 of this call lies in the multicast mapping of the matrix)."""
+        got = C.c_long(0)
+        self.ctx.L.check(self.ctx.lib.jdsp_mfcc_frames_i16_multicast_dev(self.ctx.h, self.h, _ptr(d_in), C.c_long(in_pitch), C.c_long(n_utts),
+                                                                         C.c_long(n_samples), _ptr(mc_dest), C.c_long(feat_pitch), C.byref(got)))
         return got.value
 
     def run_scatter(self, d_in, in_pitch, n_utts, n_samples, dests, feat_pitch) -> int:

@@ -351,7 +351,7 @@ template <int NC, int MU> static int launch_mfcc(jdsp_ctx *c, const MfccArgs &a)
 
 // d_feat (one matrix) or n_dest > 0 destinations (scatter form: this GPU's matrix and its peers')
 static int mfcc_frames_dev(jdsp_ctx *c, jdsp_mfcc_plan *pl, const int16_t *d_in, long in_pitch, long n_utts, long n_samples,
-                           float *d_feat, int n_dest, float *const *d_dest, long feat_pitch, long *n_frames) {
+                           float *d_feat, int n_dest, float *const *d_dest, long feat_pitch, long *n_frames, int multicast = 0) {
     REQUIRE(c && pl && d_in, "null argument");
     const jdsp_mfcc_params &p = pl->p;
     const long nf = n_samples >= p.frame_len ? (n_samples - p.frame_len) / p.hop + 1 : 0;
@@ -370,7 +370,7 @@ static int mfcc_frames_dev(jdsp_ctx *c, jdsp_mfcc_plan *pl, const int16_t *d_in,
     MfccArgs a;
     a.in = d_in; a.in_pitch = in_pitch; a.n_utts = n_utts; a.n_frames = nf;
     a.feat = d_feat; a.feat_pitch = feat_pitch; a.win_half = pl->d_win_half; a.tw = (const cf *)tw; a.twr = (const float2 *)twr;
-    a.n_dest = n_dest;
+    a.n_dest = n_dest; a.multicast = multicast;
     for (int i = 0; i < MFCC_MAX_DEST; ++i) a.dest[i] = i < n_dest ? d_dest[i] : nullptr;
     a.tri = pl->d_tri; a.chan_tab = (const int2 *)pl->d_chan_tab; a.grp_len = pl->d_grp_len; a.dct = pl->d_dct;
     a.frame_len = p.frame_len; a.hop = p.hop; a.n_mel = p.n_mel; a.n_cep = p.n_cep; a.preemph = (float)p.preemph;
@@ -388,6 +388,12 @@ extern "C" {
 int jdsp_mfcc_frames_i16_dev(jdsp_ctx *c, jdsp_mfcc_plan *pl, const int16_t *d_in, long in_pitch, long n_utts, long n_samples,
                              float *d_feat, long feat_pitch, long *n_frames) {
     return mfcc_frames_dev(c, pl, d_in, in_pitch, n_utts, n_samples, d_feat, 0, nullptr, feat_pitch, n_frames);
+}
+int jdsp_mfcc_frames_i16_multicast_dev(jdsp_ctx *c, jdsp_mfcc_plan *pl, const int16_t *d_in, long in_pitch, long n_utts, long n_samples,
+                                       float *d_mc_dest, long feat_pitch, long *n_frames) {
+    REQUIRE(d_mc_dest, "null multicast destination");
+    float *const one[1] = {d_mc_dest};
+    return mfcc_frames_dev(c, pl, d_in, in_pitch, n_utts, n_samples, nullptr, 1, one, feat_pitch, n_frames, 1);
 }
 int jdsp_mfcc_frames_i16_scatter_dev(jdsp_ctx *c, jdsp_mfcc_plan *pl, const int16_t *d_in, long in_pitch, long n_utts, long n_samples,
                                      int n_dest, float *const *d_dest, long feat_pitch, long *n_frames) {

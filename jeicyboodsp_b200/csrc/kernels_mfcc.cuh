@@ -42,6 +42,9 @@ struct MfccArgs {
     // collective after the kernel.  dest[d] points at utterance 0 of THIS launch inside matrix d; all share feat_pitch.
     float *dest[8];
     int n_dest;
+    // multicast != 0: dest[0] (n_dest == 1) is an NVLink MULTICAST address (an NVSwitch multicast object bound to the same offset of every
+    // GPU's matrix): one multimem.st leaves this GPU and the switch replicates it into all copies, this GPU's included
+    int multicast;
 };
 constexpr int MFCC_MAX_DEST = 8;
 
@@ -72,6 +75,22 @@ struct MfccGeom {
     static_assert(NC / 2 / G == 8, "eight bin pairs per thread");
     static_assert(OFF_MAG % 16 == 0 && OFF_TW % 16 == 0, "16-byte rows");
 };
+
+// store to a multicast address (the switch replicates it to every GPU bound to the multicast object)
+JDSP_DEV void multimem_st2(float *p, float2 v) {
+#ifdef JDSP_EMUL
+    *reinterpret_cast<float2 *>(p) = v;
+#else
+    asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+#endif
+}
+JDSP_DEV void multimem_st1(float *p, float v) {
+#ifdef JDSP_EMUL
+    *p = v;
+#else
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+#endif
+}
 
 JDSP_DEV float log_fast(float x) {
 #ifdef JDSP_EMUL
@@ -266,6 +285,16 @@ __global__ void __launch_bounds__(MfccGeom<NC>::NT, 2) mfcc_kernel(MfccArgs a) {
             __syncthreads();
             const long off = dm.q * feat_pitch + (long)dm.r * FB * NCEP;
             const int nfl = nfb * NCEP;
+            if (a.multicast) {      // one copy leaves the GPU: the whole CTA writes the run once (at most one 8-byte store per thread)
+                float *dp = a.dest[0] + off;
+                if ((reinterpret_cast<uintptr_t>(dp) & 7) == 0) {
+                    const float2 *sp2 = reinterpret_cast<const float2 *>(stage);
+                    for (int i = tid; i < nfl / 2; i += NT) multimem_st2(dp + 2 * i, sp2[i]);
+                    if ((nfl & 1) && tid == 0) multimem_st1(dp + nfl - 1, stage[nfl - 1]);
+                } else {
+                    for (int i = tid; i < nfl; i += NT) multimem_st1(dp + i, stage[i]);
+                }
+            } else
             for (int d = warp; d < n_dest; d += NW) {
                 float *dp = a.dest[d] + off;
                 if ((reinterpret_cast<uintptr_t>(dp) & 7) == 0) {

@@ -91,3 +91,27 @@ class PeerMatrix:
             dist.barrier()           # every mapping of this rank's copy is gone before it is freed
         self.ctx.free(self.local)
         self.addrs, self.local = [], 0
+
+
+class MulticastMatrix:
+    """The same matrix in torch's symmetric memory, which also binds all copies to ONE NVSwitch multicast address: `dest(unit0)`
+    is handed to MfccPlan.run_multicast, whose kernel stores each feature row once and lets the switch replicate it into every
+    GPU's copy.  `available()` is False where the platform has no multicast (then use PeerMatrix).  Collective constructor."""
+
+    def __init__(self, n_units_total: int, row_floats: int, device):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.n_units, self.row = n_units_total, row_floats
+        self.t = symm_mem.empty(n_units_total * row_floats, dtype=torch.float32, device=device)
+        self.hdl = symm_mem.rendezvous(self.t, dist.group.WORLD.group_name)
+        self.mc = int(self.hdl.multicast_ptr)
+
+    def available(self) -> bool:
+        return self.mc != 0
+
+    def dest(self, unit0: int) -> int:
+        return self.mc + unit0 * self.row * 4
+
+    def tensor(self):
+        return self.t.view(self.n_units, self.row)

@@ -526,7 +526,11 @@ def test_mfcc_scatter_form_equals_plain(be, pad):
     for m in mats:
         m[...] = -7.0
     assert plan.run_scatter(d_in, n, U, n, [m[u0:] for m in mats], pitch) == nf
-    for m in mats:
+    # the multicast form issues multimem.st to ONE address; on an ordinary address that is a strong store: same rows, same place
+    mc = be.zeros((total_u, pitch), np.float32)
+    mc[...] = -7.0
+    assert plan.run_multicast(d_in, n, U, n, mc[u0:], pitch) == nf
+    for m in mats + [mc]:
         got = be.to_host(m)
         assert np.array_equal(got[u0:u0 + U, : nf * 13], plain[:, : nf * 13])
         assert np.all(got[:u0] == -7.0) and np.all(got[u0 + U:] == -7.0) and np.all(got[:, nf * 13:] == -7.0)

@@ -68,6 +68,29 @@ M = pm.tensor().view(U_total, nf, 13)
 same = bool(torch.equal(M, ref[0]))
 ok = torch.tensor([0.0 if same else 1.0], device=dev)
 dist.all_reduce(ok, op=dist.ReduceOp.MAX)
+# ---- the same through ONE NVLink multicast address (torch symmetric memory binds every rank's copy to an NVSwitch multicast object) ----
+from jeicyboodsp_b200.sharding import MulticastMatrix  # noqa: E402
+mc_line = "multicast: not available on this platform"
+try:
+    mm = MulticastMatrix(U_total, nf * 13, dev)
+    if mm.available():
+        mcd = mm.dest(lo)
+
+        def fused_mc():
+            plan.run_multicast(x, n, U, n, mcd, nf * 13)
+            dist.all_reduce(tiny)
+
+        ms_mc = timed(fused_mc)
+        torch.cuda.synchronize(); dist.barrier()
+        same_mc = bool(torch.equal(mm.tensor().view(U_total, nf, 13), ref[0]))
+        okm = torch.tensor([0.0 if same_mc else 1.0], device=dev)
+        dist.all_reduce(okm, op=dist.ReduceOp.MAX)
+        ok = torch.maximum(ok, okm)
+        mc_line = f"fused multicast scatter (multimem.st, + 1-element all-reduce) {ms_mc:.3f} ms, identical on every rank: {okm.item() == 0.0}"
+except Exception as e:  # noqa: BLE001 - platforms without symmetric memory / multicast
+    mc_line = f"multicast: {type(e).__name__}: {e}"
+if rank == 0:
+    print(mc_line, flush=True)
 if rank == 0:
     print(f"world {world}: {U_total} utterances x 10 s; kernel only {ms_kernel:.3f} ms, kernel + NCCL all-gather {ms_nccl:.3f} ms, "
           f"fused scatter (+ 1-element all-reduce) {ms_fused:.3f} ms; every rank's matrix identical to the NCCL result: {ok.item() == 0.0}", flush=True)
