@@ -20,5 +20,5 @@ PY
 timeout 900 python bench.py --impl reference > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err; echo "ref rc=$?"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_launches_$TAG.log 2>&1; echo "launch list rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:denoise_stream -s 2 -c 2 -o gpurun_out/ncu_denoise_$TAG python tools/prof_denoise.py --streams 4096 --seconds 4 --iters 2 > gpurun_out/ncu_denoise_$TAG.log 2>&1; echo "ncu denoise rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"mfcc_kernel|fastconv_stream" -s 2 -c 2 -o gpurun_out/ncu_small_$TAG python tools/prof_small.py --which mfcc,fastconv --iters 2 > gpurun_out/ncu_small_$TAG.log 2>&1; echo "ncu mfcc/fastconv rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"mfcc_kernel|fastconv_stream" -s 1 -c 2 -o gpurun_out/ncu_small_$TAG python tools/prof_small.py --which mfcc,fastconv --iters 2 > gpurun_out/ncu_small_$TAG.log 2>&1; echo "ncu mfcc/fastconv rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:roundtrip_warp -s 1 -c 1 -o gpurun_out/ncu_rt_$TAG python tools/prof_roundtrip.py > gpurun_out/ncu_rt_$TAG.log 2>&1; echo "ncu roundtrip rc=$?"
