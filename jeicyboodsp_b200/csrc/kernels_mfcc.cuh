@@ -279,31 +279,42 @@ __global__ void __launch_bounds__(MfccGeom<NC>::NT, 2) mfcc_kernel(MfccArgs a) {
             }
         }
         if (SCATTER) {
-            // ---- scatter: the batch's rows are ONE contiguous run of nfb * n_cep floats in every destination matrix; warp d writes the run
-            // to destination d with whole-warp 8-byte stores (256 contiguous bytes per instruction: full sectors locally, full NVLink
-            // write packets to a peer), straight from the staged copy.  The next batch's B2 writes `stage` two barriers from here.
+            // ---- scatter: the batch's rows are ONE contiguous run of nfb * n_cep floats in every destination matrix; the warps that did B2
+            // write the run to the destinations (warp w: destinations w, w + nb2, ...) with whole-warp 8-byte stores (256 contiguous bytes per
+            // instruction: full sectors locally, full NVLink write packets to a peer), straight from the staged copy.  Only those warps meet
+            // at a named barrier: the others are already in the next batch's Phase A (a CTA-wide barrier here cost 8 % of the kernel).  The
+            // next batch's B2 writes `stage` two CTA barriers from here, after every copying warp has arrived at them.
+            const int nb2 = (NCEP + CPW - 1) / CPW;          // warps 0 .. nb2-1 hold the cepstra
+#ifdef JDSP_EMUL
             __syncthreads();
-            const long off = dm.q * feat_pitch + (long)dm.r * FB * NCEP;
-            const int nfl = nfb * NCEP;
-            if (a.multicast) {      // one copy leaves the GPU: the whole CTA writes the run once (at most one 8-byte store per thread)
-                float *dp = a.dest[0] + off;
-                if ((reinterpret_cast<uintptr_t>(dp) & 7) == 0) {
-                    const float2 *sp2 = reinterpret_cast<const float2 *>(stage);
-                    for (int i = tid; i < nfl / 2; i += NT) multimem_st2(dp + 2 * i, sp2[i]);
-                    if ((nfl & 1) && tid == 0) multimem_st1(dp + nfl - 1, stage[nfl - 1]);
+#else
+            if (warp < nb2) asm volatile("bar.sync 1, %0;" ::"r"(nb2 * 32) : "memory");
+#endif
+            if (warp < nb2) {
+                const long off = dm.q * feat_pitch + (long)dm.r * FB * NCEP;
+                const int nfl = nfb * NCEP;
+                const int nt2 = nb2 * 32;
+                if (a.multicast) {      // one copy leaves the GPU: the B2 warps write the run once
+                    float *dp = a.dest[0] + off;
+                    if ((reinterpret_cast<uintptr_t>(dp) & 7) == 0) {
+                        const float2 *sp2 = reinterpret_cast<const float2 *>(stage);
+                        for (int i = tid; i < nfl / 2; i += nt2) multimem_st2(dp + 2 * i, sp2[i]);
+                        if ((nfl & 1) && tid == 0) multimem_st1(dp + nfl - 1, stage[nfl - 1]);
+                    } else {
+                        for (int i = tid; i < nfl; i += nt2) multimem_st1(dp + i, stage[i]);
+                    }
                 } else {
-                    for (int i = tid; i < nfl; i += NT) multimem_st1(dp + i, stage[i]);
-                }
-            } else
-            for (int d = warp; d < n_dest; d += NW) {
-                float *dp = a.dest[d] + off;
-                if ((reinterpret_cast<uintptr_t>(dp) & 7) == 0) {
-                    float2 *dp2 = reinterpret_cast<float2 *>(dp);
-                    const float2 *sp2 = reinterpret_cast<const float2 *>(stage);
-                    for (int i = lane; i < nfl / 2; i += 32) dp2[i] = sp2[i];
-                    if ((nfl & 1) && lane == 0) dp[nfl - 1] = stage[nfl - 1];
-                } else {
-                    for (int i = lane; i < nfl; i += 32) dp[i] = stage[i];
+                    for (int d = warp; d < n_dest; d += nb2) {
+                        float *dp = a.dest[d] + off;
+                        if ((reinterpret_cast<uintptr_t>(dp) & 7) == 0) {
+                            float2 *dp2 = reinterpret_cast<float2 *>(dp);
+                            const float2 *sp2 = reinterpret_cast<const float2 *>(stage);
+                            for (int i = lane; i < nfl / 2; i += 32) dp2[i] = sp2[i];
+                            if ((nfl & 1) && lane == 0) dp[nfl - 1] = stage[nfl - 1];
+                        } else {
+                            for (int i = lane; i < nfl; i += 32) dp[i] = stage[i];
+                        }
+                    }
                 }
             }
         }
