@@ -171,6 +171,39 @@ __global__ void __launch_bounds__(MfccGeom<NC>::NT, 2) mfcc_kernel(MfccArgs a) {
             for (int i = 0; i < nf; ++i) bulk_g2s(xs + i * SLOT, src + (long)i * hop, (unsigned)(W * 2), bar);
         }
     };
+    // ---- scatter form: the rows of a batch are ONE contiguous run of nfb * n_cep floats in every destination matrix.  B2 stages them; they
+    // leave one CTA barrier later -- right after the barrier that ends the NEXT batch's Phase A, which already orders B2's writes before
+    // every warp -- so the scatter adds no barrier of its own, and all eight warps share the copy: warp d writes the run to destination d
+    // (d, d + 8, ...) with whole-warp 8-byte stores, 256 contiguous bytes per instruction (full sectors locally, full NVLink write packets
+    // to a peer).  `stage` is rewritten by the next B2, one more CTA barrier away.  (History: a barrier right after B2 + copy by all warps
+    // cost 8 % locally; a named barrier among the four B2 warps + copy by those four cost 1.3 % locally but MORE over NVLink -- 3.52 against
+    // 3.42 ms at 8 GPUs -- because four warps then sit behind fourteen remote stores each.)
+    long pend_off = 0;
+    int pend_nfl = 0;
+    auto copy_out = [&]() {
+        if (a.multicast) {      // one copy leaves the GPU (the NVSwitch replicates it): at most one 8-byte store per thread
+            float *dp = a.dest[0] + pend_off;
+            if ((reinterpret_cast<uintptr_t>(dp) & 7) == 0) {
+                const float2 *sp2 = reinterpret_cast<const float2 *>(stage);
+                for (int i = tid; i < pend_nfl / 2; i += NT) multimem_st2(dp + 2 * i, sp2[i]);
+                if ((pend_nfl & 1) && tid == 0) multimem_st1(dp + pend_nfl - 1, stage[pend_nfl - 1]);
+            } else {
+                for (int i = tid; i < pend_nfl; i += NT) multimem_st1(dp + i, stage[i]);
+            }
+            return;
+        }
+        for (int d = warp; d < n_dest; d += NW) {
+            float *dp = a.dest[d] + pend_off;
+            if ((reinterpret_cast<uintptr_t>(dp) & 7) == 0) {
+                float2 *dp2 = reinterpret_cast<float2 *>(dp);
+                const float2 *sp2 = reinterpret_cast<const float2 *>(stage);
+                for (int i = lane; i < pend_nfl / 2; i += 32) dp2[i] = sp2[i];
+                if ((pend_nfl & 1) && lane == 0) dp[pend_nfl - 1] = stage[pend_nfl - 1];
+            } else {
+                for (int i = lane; i < pend_nfl; i += 32) dp[i] = stage[i];
+            }
+        }
+    };
     StridedDivmod dm((long)blockIdx.x, (long)gridDim.x, batches_per_utt), dn = dm;
     if (warp == 0 && (long)blockIdx.x < n_batches) fetch(dm.q, dm.r);
     unsigned phase = 0;
@@ -231,6 +264,7 @@ __global__ void __launch_bounds__(MfccGeom<NC>::NT, 2) mfcc_kernel(MfccArgs a) {
             dn.next();
             if (batch + gridDim.x < n_batches) fetch(dn.q, dn.r);
         }
+        if (SCATTER && pend_nfl > 0) copy_out();   // the PREVIOUS batch's rows (staged before the barrier above)
         // =================================== Phase B ===================================
         // ---- B1 MelFilterBank (:154-174), ln (:170-172): channel 4*warp + lane/8, frames 4*(lane%8) .. +3 ----------------------------
         for (int c0 = 4 * warp; c0 < C; c0 += 4 * NW) {
@@ -278,48 +312,16 @@ __global__ void __launch_bounds__(MfccGeom<NC>::NT, 2) mfcc_kernel(MfccArgs a) {
                     if (warp * CPW + i < NCEP) stage[lane * NCEP + warp * CPW + i] = acc[i];
             }
         }
-        if (SCATTER) {
-            // ---- scatter: the batch's rows are ONE contiguous run of nfb * n_cep floats in every destination matrix; the warps that did B2
-            // write the run to the destinations (warp w: destinations w, w + nb2, ...) with whole-warp 8-byte stores (256 contiguous bytes per
-            // instruction: full sectors locally, full NVLink write packets to a peer), straight from the staged copy.  Only those warps meet
-            // at a named barrier: the others are already in the next batch's Phase A (a CTA-wide barrier here cost 8 % of the kernel).  The
-            // next batch's B2 writes `stage` two CTA barriers from here, after every copying warp has arrived at them.
-            const int nb2 = (NCEP + CPW - 1) / CPW;          // warps 0 .. nb2-1 hold the cepstra
-#ifdef JDSP_EMUL
-            __syncthreads();
-#else
-            if (warp < nb2) asm volatile("bar.sync 1, %0;" ::"r"(nb2 * 32) : "memory");
-#endif
-            if (warp < nb2) {
-                const long off = dm.q * feat_pitch + (long)dm.r * FB * NCEP;
-                const int nfl = nfb * NCEP;
-                const int nt2 = nb2 * 32;
-                if (a.multicast) {      // one copy leaves the GPU: the B2 warps write the run once
-                    float *dp = a.dest[0] + off;
-                    if ((reinterpret_cast<uintptr_t>(dp) & 7) == 0) {
-                        const float2 *sp2 = reinterpret_cast<const float2 *>(stage);
-                        for (int i = tid; i < nfl / 2; i += nt2) multimem_st2(dp + 2 * i, sp2[i]);
-                        if ((nfl & 1) && tid == 0) multimem_st1(dp + nfl - 1, stage[nfl - 1]);
-                    } else {
-                        for (int i = tid; i < nfl; i += nt2) multimem_st1(dp + i, stage[i]);
-                    }
-                } else {
-                    for (int d = warp; d < n_dest; d += nb2) {
-                        float *dp = a.dest[d] + off;
-                        if ((reinterpret_cast<uintptr_t>(dp) & 7) == 0) {
-                            float2 *dp2 = reinterpret_cast<float2 *>(dp);
-                            const float2 *sp2 = reinterpret_cast<const float2 *>(stage);
-                            for (int i = lane; i < nfl / 2; i += 32) dp2[i] = sp2[i];
-                            if ((nfl & 1) && lane == 0) dp[nfl - 1] = stage[nfl - 1];
-                        } else {
-                            for (int i = lane; i < nfl; i += 32) dp[i] = stage[i];
-                        }
-                    }
-                }
-            }
+        if (SCATTER) {   // the staged rows leave after the next CTA barrier (see copy_out)
+            pend_off = dm.q * feat_pitch + (long)dm.r * FB * NCEP;
+            pend_nfl = nfb * NCEP;
         }
         // no barrier here: the next batch's Phase A touches the exchange buffers and mag, which B2 does not read, and its B1 rewrites
         // logmel only after the barrier that follows that Phase A
+    }
+    if (SCATTER && pend_nfl > 0) {   // the CTA's last batch
+        __syncthreads();
+        copy_out();
     }
 }
 
