@@ -78,10 +78,13 @@ class PeerMatrix:
         raw.__cuda_array_interface__ = {"shape": (self.n_units, self.row), "typestr": "<f4", "data": (self.local, False), "version": 3, "strides": None}
         return torch.as_tensor(raw, device=f"cuda:{torch.cuda.current_device()}")
 
-    def close(self) -> None:
+    def close(self, collective: bool = True) -> None:
+        """collective=False: tear down this rank's side only (construction failed on another rank; nothing was written)."""
         import torch
         import torch.distributed as dist
         torch.cuda.synchronize()
+        if not collective:
+            self.world = 1
         if self.world > 1:
             dist.barrier()           # nobody unmaps or frees while a peer may still be writing
         for r, a in enumerate(self.addrs):
