@@ -80,9 +80,8 @@ class PeerMatrix:
 
     def close(self, collective: bool = True) -> None:
         """collective=False: tear down this rank's side only (construction failed on another rank; nothing was written)."""
-        import torch
         import torch.distributed as dist
-        torch.cuda.synchronize()
+        self.ctx.sync()              # this rank's kernels (the writers into the peers' copies) have finished
         if not collective:
             self.world = 1
         if self.world > 1:

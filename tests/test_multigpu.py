@@ -43,6 +43,31 @@ def test_two_shards_scatter_into_both_copies(be):
     plan.close()
 
 
+def test_peer_matrix_single_rank_on_the_emulator():
+    """sharding.PeerMatrix with no process group (world 1): allocation through the C ABI, the destination address of a unit, the scatter
+    form writing into it, teardown.  (The emulator's device memory is host memory, so the result is read back through ctypes.)"""
+    import ctypes as C
+
+    from jeicyboodsp_b200.sharding import PeerMatrix
+    be = _CACHE.setdefault("emul", EmulBackend())
+    p = be.L.mfcc_params("bench")
+    n, total, u0 = 6000, 4, 1
+    plan = be.ctx.mfcc_plan(p)
+    nf = plan.n_frames(n)
+    row = nf * 13
+    x = np.stack([synth.mfcc_utterance(90 + u, n) for u in range(2)])
+    plain = be.zeros((2, row), np.float32)
+    plan.run(be.to_dev(x), n, 2, n, plain, row)
+    pm = PeerMatrix(be.ctx, total, row)
+    assert pm.world == 1 and len(pm.addrs) == 1 and pm.dests(u0) == [pm.local + u0 * row * 4]
+    C.memset(pm.local, 0, pm.nbytes)
+    assert plan.run_scatter(be.to_dev(x), n, 2, n, pm.dests(u0), row) == nf
+    got = np.ctypeslib.as_array((C.c_float * (total * row)).from_address(pm.local)).reshape(total, row).copy()
+    assert np.array_equal(got[u0:u0 + 2], plain) and not got[:u0].any() and not got[u0 + 2:].any()
+    pm.close()
+    plan.close()
+
+
 @pytest.mark.gpu
 def test_fused_scatter_two_gpus_equals_nccl_allgather():
     import torch
